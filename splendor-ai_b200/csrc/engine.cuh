@@ -1,0 +1,894 @@
+// engine.cuh -- device-side Splendor rules for sm_100a: packed state words, SWAR helpers, legal-action
+// count / select / membership, action application, terminal test and scoring.
+//
+// Rule semantics follow the reference (paths relative to /root/reference/src/splendor/):
+//   getLegalActions      splendor/splendor_model.py:404-576   generate_return_combos :329-367
+//   resources_sufficient splendor/splendor_model.py:371-394   noble_visit            :397-402
+//   generateSuccessor    splendor/splendor_model.py:222-295   GameRule.update template.py:47-53
+//   gameEnds / calScore  splendor/splendor_model.py:299-323   LimitRoundsGameRule splendor/utils.py:14-25
+//   ALL_ACTIONS order    splendor/gym/envs/actions.py:109-237
+// but the formulation is different on purpose: the reference materialises a list of dicts; here every count is a
+// closed form over a handful of 32-bit words, so that one thread can play one game entirely out of registers.
+//
+// Word format ("g6"): six 5-bit fields in the reference's COLOURS order (splendor_utils.py:124-131)
+//   field 0 black, 1 red, 2 yellow, 3 green, 4 blue, 5 white; every value is <= 15, bit 4 of each field is a guard
+//   bit, which makes per-field saturating subtraction and >= tests a three-instruction SWAR operation.
+#pragma once
+#include <stdint.h>
+#ifndef SPL_HOSTSIM  // tests/hostsim compiles this header with g++ and its own shims (test only)
+#include <cuda_runtime.h>
+#endif
+
+#include "../../include/spl_tables.h"
+#include "../../include/splendor_b200.h"
+
+namespace spl {
+
+constexpr uint32_t ONES6 = 0x02108421u;        // 1 in each field
+constexpr uint32_t H6 = ONES6 << 4;            // guard bit of each field
+constexpr uint32_t NORMAL_FIELDS = 0x3Bu;      // fields 0,1,3,4,5 (everything but yellow)
+constexpr int YSH = 10;                        // bit offset of the yellow field
+constexpr uint32_t NONE8 = 0xFFu;
+
+__host__ __device__ constexpr int field_of_normal(int c) { return c + (c >= 2 ? 1 : 0); }  // NORMAL_COLORS idx -> field
+__host__ __device__ constexpr int field_of_colour_id(int c) { return c == 5 ? 2 : (c >= 2 ? c + 1 : c); }
+
+// ------------------------------------------------------------------------------------------------ static tables
+enum ActType { T_PASS = 0, T_RESERVE = 1, T_SAME = 2, T_DIFF = 3, T_BUY_RESERVE = 4, T_BUY_AVAILABLE = 5 };
+constexpr int BASE_RESERVE = 6, BASE_SAME = 510, BASE_DIFF = 1140, BASE_BUY_RESERVE = 3420, BASE_BUY_AVAILABLE = 3438;
+
+struct Tables {
+    uint2 card[96];          // .x = cost (g6, yellow field 0) ; .y = 5*colour_field | points << 5 | tier << 8
+    uint32_t noble[16];      // requirement (g6); entry 15 = "no noble" (unsatisfiable)
+    uint32_t combo_c[25];    // collect_diff combo ci: collected gems (g6).  ci 0..4 L=1, 5..14 L=2, 15..24 L=3
+    uint16_t combo_base[25]; // ALL_ACTIONS index of (combo ci, noble slot 0, variant 0)
+    uint16_t combo_off[25];  // first entry of the combo's variants in ret_diff
+    uint8_t combo_mask[25];  // 6-bit field mask of the combo's colours
+    uint8_t pad[3];
+    uint32_t ret_diff[380];  // returned gems (g6) of variant v: 6 / 15 / 20 variants per combo of length 1 / 2 / 3
+    uint32_t ret_same[105];  // [c*21 + v], c = NORMAL_COLORS index
+};
+
+namespace detail {
+struct CardRow { int colour, points, c[5]; };
+struct NobleRow { int c[5]; };
+constexpr CardRow CARD_ROWS[SPL_NUM_CARDS] = {
+#define X(col, pts, c0, c1, c2, c3, c4) {col, pts, {c0, c1, c2, c3, c4}},
+    SPL_CARD_ROWS
+#undef X
+};
+constexpr NobleRow NOBLE_ROWS[SPL_NUM_NOBLES] = {
+#define X(c0, c1, c2, c3, c4) {{c0, c1, c2, c3, c4}},
+    SPL_NOBLE_ROWS
+#undef X
+};
+__host__ __device__ constexpr uint32_t g6_from_normal(const int *c)
+{
+    uint32_t w = 0;
+    for (int i = 0; i < 5; i++) w |= (uint32_t)c[i] << (5 * field_of_normal(i));
+    return w;
+}
+}  // namespace detail
+
+// itertools.combinations / combinations_with_replacement orders of gym/envs/actions.py:145-199, unrolled at compile time
+__host__ __device__ constexpr Tables make_tables()
+{
+    Tables T{};
+    for (int i = 0; i < 96; i++) T.card[i] = uint2{0x1EF7BDEFu & ~(31u << YSH), 0};  // filler: costs 15 of everything
+    for (int i = 0; i < SPL_NUM_CARDS; i++) {
+        const detail::CardRow &r = detail::CARD_ROWS[i];
+        int tier = i < 40 ? 0 : (i < 70 ? 1 : 2);
+        T.card[i].x = detail::g6_from_normal(r.c);
+        T.card[i].y = (uint32_t)(5 * field_of_colour_id(r.colour)) | ((uint32_t)r.points << 5) | ((uint32_t)tier << 8);
+    }
+    for (int i = 0; i < 16; i++) T.noble[i] = 0x1EF7BDEFu & ~(31u << YSH);  // 15 of everything: never satisfied
+    for (int i = 0; i < SPL_NUM_NOBLES; i++) T.noble[i] = detail::g6_from_normal(detail::NOBLE_ROWS[i].c);
+
+    // collect_same variants (actions.py:145-174): none | pairs of the 5 other colours | one of | two of
+    for (int c = 0; c < 5; c++) {
+        int others[5] = {0, 0, 0, 0, 0}, k = 0;
+        for (int f = 0; f < 6; f++)
+            if (f != field_of_normal(c)) others[k++] = f;
+        uint32_t *row = T.ret_same + c * 21;
+        int v = 0;
+        row[v++] = 0;
+        for (int i = 0; i < 5; i++)
+            for (int j = i + 1; j < 5; j++) row[v++] = (1u << (5 * others[i])) + (1u << (5 * others[j]));
+        for (int i = 0; i < 5; i++) row[v++] = 1u << (5 * others[i]);
+        for (int i = 0; i < 5; i++) row[v++] = 2u << (5 * others[i]);
+    }
+    // collect_diff (actions.py:177-199)
+    int ci = 0, off = 0, base = BASE_DIFF;
+    for (int L = 1; L <= 3; L++) {
+        const int V = L == 1 ? 6 : (L == 2 ? 15 : 20);
+        for (int a = 0; a < 5; a++)
+            for (int b = (L >= 2 ? a + 1 : 4); b < 5; b++)
+                for (int c = (L >= 3 ? b + 1 : 4); c < 5; c++) {
+                    uint32_t fmask = 1u << field_of_normal(a);
+                    if (L >= 2) fmask |= 1u << field_of_normal(b);
+                    if (L >= 3) fmask |= 1u << field_of_normal(c);
+                    uint32_t cw = 0;
+                    int others[6] = {0, 0, 0, 0, 0, 0}, k = 0;
+                    for (int f = 0; f < 6; f++) {
+                        if (fmask >> f & 1) cw |= 1u << (5 * f);
+                        else others[k++] = f;
+                    }
+                    T.combo_c[ci] = cw;
+                    T.combo_mask[ci] = (uint8_t)fmask;
+                    T.combo_base[ci] = (uint16_t)base;
+                    T.combo_off[ci] = (uint16_t)off;
+                    int v = 0;
+                    T.ret_diff[off + v++] = 0;
+                    for (int r = 1; r <= L; r++)
+                        for (int x = 0; x < k; x++)
+                            for (int y = (r >= 2 ? x : k - 1); y < k; y++)
+                                for (int z = (r >= 3 ? y : k - 1); z < k; z++) {
+                                    uint32_t w = 1u << (5 * others[x]);
+                                    if (r >= 2) w += 1u << (5 * others[y]);
+                                    if (r >= 3) w += 1u << (5 * others[z]);
+                                    T.ret_diff[off + v++] = w;
+                                }
+                    ci++;
+                    off += V;
+                    base += 6 * V;
+                }
+    }
+    return T;
+}
+
+// ------------------------------------------------------------------------------------------------ SWAR helpers
+__device__ __forceinline__ uint32_t satsub6(uint32_t a, uint32_t b)  // per field max(a-b,0); fields < 16
+{
+    uint32_t d = (a | H6) - b;
+    uint32_t m = d & H6;
+    m -= m >> 4;
+    return d & m;
+}
+__device__ __forceinline__ uint32_t hsum6(uint32_t x)  // sum of the six fields (each <= 15)
+{
+    x = (x & 0x7FFFu) + (x >> 15);
+    return (x & 31u) + ((x >> 5) & 31u) + (x >> 10);
+}
+__device__ __forceinline__ uint32_t compress6(uint32_t h)  // guard bits (subset of H6) -> 6-bit field mask
+{
+    return ((((h >> 4) & 0x00108421u) * 0x00111110u) >> 20 & 31u) | ((h >> 24) & 32u);
+}
+__device__ __forceinline__ uint32_t ge_mask(uint32_t x, uint32_t t)  // fields with value >= t (1 <= t <= 15)
+{
+    return compress6((x + (16u - t) * ONES6) & H6);
+}
+__device__ __forceinline__ uint32_t field(uint32_t w, int sh) { return (w >> sh) & 31u; }
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+__device__ __forceinline__ uint32_t set_byte(uint32_t w, int i, uint32_t v)
+{
+    return (w & ~(0xFFu << (8 * i))) | (v << (8 * i));
+}
+__device__ __forceinline__ int select_bit(uint32_t m, int j)  // position of the j-th (0-based) set bit; m has > j bits
+{
+    int pos = 0, c;
+    c = __popc(m & 0xFFFFu); if (j >= c) { j -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xFFu);   if (j >= c) { j -= c; pos += 8;  m >>= 8; }
+    c = __popc(m & 0xFu);    if (j >= c) { j -= c; pos += 4;  m >>= 4; }
+    c = __popc(m & 0x3u);    if (j >= c) { j -= c; pos += 2;  m >>= 2; }
+    if (j >= (int)(m & 1u)) pos += 1;
+    return pos;
+}
+__device__ __forceinline__ int select_bit8(uint32_t m, int j)  // same for masks of <= 8 bits
+{
+    int pos = 0, c;
+    c = __popc(m & 0xFu); if (j >= c) { j -= c; pos += 4; m >>= 4; }
+    c = __popc(m & 0x3u); if (j >= c) { j -= c; pos += 2; m >>= 2; }
+    if (j >= (int)(m & 1u)) pos += 1;
+    return pos;
+}
+__device__ __forceinline__ int small_div(int k, int d)  // floor(k/d) for 0 <= k < 8192, 1 <= d <= 64
+{
+    return (int)__fdividef((float)k + 0.5f, (float)d);
+}
+__device__ __forceinline__ uint32_t occupied4(uint32_t dealt_word)  // 4-bit mask of non-empty slots (ids < 128, empty 0xFF)
+{
+    return ((((~dealt_word) & 0x80808080u) >> 7) * 0x00204081u) >> 21 & 15u;
+}
+
+// Philox4x32-10 (Salmon et al. 2011).  counter = (game lo, game hi, index, stream), key = seed.
+__device__ __forceinline__ uint4 philox(uint64_t seed, uint64_t game, uint32_t index, uint32_t stream)
+{
+    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = index, c3 = stream;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+enum Stream { STREAM_ACTION = 0, STREAM_DECK0 = 1, STREAM_NOBLES = 4, STREAM_ENV = 5 };
+
+// ------------------------------------------------------------------------------------------------ state in registers
+constexpr uint32_t META_EXPLICIT = 1u << 24, META_ILLEGAL = 1u << 26;
+
+template <int P>
+struct Env {
+    uint32_t bank, d[3], k[3], meta;          // board words 0..7
+    uint32_t pg[P], pc[P], pr[P], pi[P];      // per player: gems, bought cards, reserved ids + score, turns|nobles|passed
+};
+
+template <int P>
+__device__ __forceinline__ void load_env(Env<P> &e, const uint4 *__restrict__ st, int64_t N, int64_t i)
+{
+    uint4 a = st[i], b = st[N + i];
+    e.bank = a.x; e.d[0] = a.y; e.d[1] = a.z; e.d[2] = a.w;
+    e.k[0] = b.x; e.k[1] = b.y; e.k[2] = b.z; e.meta = b.w;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        uint4 q = st[(int64_t)(2 + p) * N + i];
+        e.pg[p] = q.x; e.pc[p] = q.y; e.pr[p] = q.z; e.pi[p] = q.w;
+    }
+}
+template <int P>
+__device__ __forceinline__ void store_env(const Env<P> &e, uint4 *__restrict__ st, int64_t N, int64_t i)
+{
+    st[i] = make_uint4(e.bank, e.d[0], e.d[1], e.d[2]);
+    st[N + i] = make_uint4(e.k[0], e.k[1], e.k[2], e.meta);
+#pragma unroll
+    for (int p = 0; p < P; p++) st[(int64_t)(2 + p) * N + i] = make_uint4(e.pg[p], e.pc[p], e.pr[p], e.pi[p]);
+}
+__device__ __forceinline__ int seat_of(uint32_t meta) { return (meta >> 20) & 3; }
+
+// per-game context a deal needs
+struct DeckSrc {
+    const uint8_t *lists;  // explicit deck lists of THIS env (90 bytes) or nullptr
+    uint64_t seed, game;
+};
+
+// BoardState.deal (splendor_model.py:95-99).  Counter-based decks: the d-th card dealt from a tier is the
+// floor(u*c)-th smallest id still in the deck (c cards left, u = Philox word of (seed, game, d, tier)) - a lazy
+// Fisher-Yates draw whose order is a function of (seed, game) only, never of the actions played.
+template <int P>
+__device__ __forceinline__ uint32_t deal(Env<P> &e, int tier, const DeckSrc &src)
+{
+    if (src.lists) {  // explicit lists: pop from the end
+        uint32_t cnt = byte_of(e.k[0], tier);
+        if (cnt == 0) return NONE8;
+        cnt--;
+        e.k[0] = set_byte(e.k[0], tier, cnt);
+        const int base = tier == 0 ? 0 : (tier == 1 ? 40 : 70);
+        return src.lists[base + cnt];
+    }
+    uint32_t lo, hi = 0;
+    int size, base;
+    if (tier == 0) { lo = e.k[0]; hi = (e.k[2] >> 20) & 0xFFu; size = 40; base = 0; }
+    else if (tier == 1) { lo = e.k[1]; size = 30; base = 40; }
+    else { lo = e.k[2] & 0xFFFFFu; size = 20; base = 70; }
+    const int clo = __popc(lo), c = clo + __popc(hi);
+    if (c == 0) return NONE8;
+    const uint32_t r = philox(src.seed, src.game, (uint32_t)(size - c), STREAM_DECK0 + tier).x;
+    int j = (int)__umulhi(r, (uint32_t)c), pos;
+    if (j < clo) {
+        pos = select_bit(lo, j);
+        if (tier == 0) e.k[0] &= ~(1u << pos);
+        else if (tier == 1) e.k[1] &= ~(1u << pos);
+        else e.k[2] &= ~(1u << pos);
+    } else {
+        pos = select_bit8(hi, j - clo);
+        e.k[2] &= ~(1u << (20 + pos));
+        pos += 32;
+    }
+    return (uint32_t)(base + pos);
+}
+
+// SplendorState.__init__ (splendor_model.py:53-93) with Philox nobles and lazily drawn decks
+template <int P>
+__device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t game)
+{
+    const uint32_t n = P == 2 ? 4 : (P == 3 ? 5 : 7);
+    e.bank = n * (ONES6 & ~(1u << YSH)) | (5u << YSH);
+    e.k[0] = 0xFFFFFFFFu; e.k[1] = 0x3FFFFFFFu; e.k[2] = 0x0FFFFFFFu;
+    // random.sample(NOBLES, P+1): partial Fisher-Yates over the 10 ids held as nibbles of a 64-bit word
+    uint64_t ids = 0x9876543210ull;
+    const uint4 r0 = philox(seed, game, 0, STREAM_NOBLES), r1 = philox(seed, game, 1, STREAM_NOBLES);
+    const uint32_t rr[5] = {r0.x, r0.y, r0.z, r0.w, r1.x};
+    uint32_t list = 0xFFFFFu;
+#pragma unroll
+    for (int i = 0; i < P + 1; i++) {
+        const int j = i + (int)__umulhi(rr[i], (uint32_t)(10 - i));
+        const uint64_t vi = (ids >> (4 * i)) & 15, vj = (ids >> (4 * j)) & 15;
+        ids = (ids & ~(15ull << (4 * i)) & ~(15ull << (4 * j))) | (vj << (4 * i)) | (vi << (4 * j));
+        list = (list & ~(15u << (4 * i))) | ((uint32_t)vj << (4 * i));
+    }
+    e.meta = list | ((uint32_t)(P - 2) << 22);
+    DeckSrc src{nullptr, seed, game};
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) w |= deal(e, t, src) << (8 * c);
+        e.d[t] = w;
+    }
+#pragma unroll
+    for (int p = 0; p < P; p++) { e.pg[p] = 0; e.pc[p] = 0; e.pr[p] = 0x00FFFFFFu; e.pi[p] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------ legal actions
+struct Choice {
+    int idx;        // ALL_ACTIONS index
+    int type;       // ActType
+    int slot;       // reserve / buy_available: board position 0..11; buy_reserve: reserved index 0..2
+    int n;          // noble slot 0 = none, k+1 = board noble at list position k
+    uint32_t C, R;  // gems collected / returned (g6); for buys R is the payment
+    uint32_t info;  // buys: Tables::card[].y of the card
+};
+
+// Everything getLegalActions derives from the state before enumerating, as a few words.
+struct Ctx {
+    uint32_t gems, cards, resv, bank;
+    uint32_t S, near;      // S: nobles already earned (bit = list position); near: bit 5*colour_field_shift+k
+    uint32_t h1, h2, h3;   // field masks: gems held >= 1 / 2 / 3
+    uint32_t A1, A4;       // field masks (normal colours): bank >= 1 / >= 4
+    uint32_t occ;          // 12-bit mask of non-empty board slots
+    int nS, hold, yellow, n_resv, nA, Lmin, Lmax;
+    bool bank_yellow;
+};
+
+template <int P>
+__device__ __forceinline__ void make_ctx(const Env<P> &e, const Tables &T, Ctx &c)
+{
+    const int seat = seat_of(e.meta);
+    c.gems = e.pg[0]; c.cards = e.pc[0]; c.resv = e.pr[0];
+#pragma unroll
+    for (int p = 1; p < P; p++)
+        if (seat == p) { c.gems = e.pg[p]; c.cards = e.pc[p]; c.resv = e.pr[p]; }
+    c.bank = e.bank;
+    // noble_visit over the board list (:430-435) + which nobles are exactly one card of one colour away (:543-554)
+    c.S = 0; c.near = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const uint32_t d = satsub6(T.noble[(e.meta >> (4 * k)) & 15u], c.cards);
+        if (d == 0) c.S |= 1u << k;
+        else if ((d & (d - 1)) == 0 && (d & ONES6)) c.near |= 1u << (__ffs(d) - 1 + k);
+    }
+    c.nS = c.S ? __popc(c.S) : 1;
+    c.hold = (int)hsum6(c.gems);
+    c.yellow = (int)field(c.gems, YSH);
+    c.h1 = ge_mask(c.gems, 1); c.h2 = ge_mask(c.gems, 2); c.h3 = ge_mask(c.gems, 3);
+    c.A1 = ge_mask(c.bank, 1) & NORMAL_FIELDS; c.A4 = ge_mask(c.bank, 4) & NORMAL_FIELDS;
+    c.bank_yellow = field(c.bank, YSH) > 0;
+    c.n_resv = __popc(~c.resv & 0x00808080u);
+    c.occ = occupied4(e.d[0]) | occupied4(e.d[1]) << 4 | occupied4(e.d[2]) << 8;
+    c.nA = __popc(c.A1);
+    c.Lmax = min(c.nA, 3);
+    c.Lmin = c.hold <= 7 ? c.Lmax : (c.hold == 8 ? min(c.nA, 2) : min(c.nA, 1));
+}
+
+// number of distinct multisets of e gems drawn from what the agent holds in the colours of field mask O (:329-367)
+__device__ __forceinline__ int n_returns(int e, const Ctx &c, uint32_t O)
+{
+    if (e <= 0) return 1;
+    const int a1 = __popc(c.h1 & O);
+    if (e == 1) return a1;
+    const int a2 = __popc(c.h2 & O);
+    if (e == 2) return (a1 * (a1 - 1) >> 1) + a2;
+    return (a1 * (a1 - 1) * (a1 - 2)) / 6 + a2 * (a1 - 1) + __popc(c.h3 & O);
+}
+// the vi-th feasible variant in [v0, v1) of a returned-gems table row
+__device__ __forceinline__ int nth_feasible(const uint32_t *row, int v0, int v1, int vi, uint32_t gems)
+{
+    int v = v0;
+    for (; v < v1; v++)
+        if (satsub6(row[v], gems) == 0 && vi-- == 0) break;
+    return v;
+}
+__device__ __forceinline__ int reserve_variants(const Ctx &c)
+{
+    return (!c.bank_yellow || c.hold < 10) ? 1 : __popc(c.h1 & NORMAL_FIELDS);
+}
+__device__ __forceinline__ int combo_len(int ci) { return ci < 5 ? 1 : (ci < 15 ? 2 : 3); }
+
+// resources_sufficient (:371-394): returns true and the payment if the card is affordable and below the 7-card cap
+__device__ __forceinline__ bool can_buy(const Ctx &c, uint2 cw, uint32_t &pay)
+{
+    const uint32_t need = satsub6(cw.x, c.cards);
+    const uint32_t shortfall = satsub6(need, c.gems);
+    const uint32_t wild = hsum6(shortfall);
+    pay = (need - shortfall) + (wild << YSH);
+    return field(c.cards, cw.y & 31u) != 7u && wild <= (uint32_t)c.yellow;
+}
+
+struct FamilyCounts { int res, same, diff, bres, bav; };
+
+template <int P>
+__device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, const Ctx &c, FamilyCounts &f)
+{
+    f.res = c.n_resv < 3 ? __popc(c.occ) * c.nS * reserve_variants(c) : 0;
+    f.same = 0;
+#pragma unroll
+    for (int n = 0; n < 5; n++) {
+        const int fl = field_of_normal(n);
+        if (c.A4 >> fl & 1) f.same += n_returns(c.hold - 8, c, 63u & ~(1u << fl));
+    }
+    f.same *= c.nS;
+    f.diff = 0;
+    if (c.hold <= 7) {
+        f.diff = (int)((0xA41110u >> (4 * c.nA)) & 15u);  // C(nA, min(nA,3)), 0 when the bank is empty
+    } else {
+        for (int ci = 0; ci < 25; ci++) {
+            const uint32_t m = T.combo_mask[ci];
+            const int L = combo_len(ci);
+            if ((m & ~c.A1) || L < c.Lmin) continue;
+            f.diff += n_returns(c.hold + L - 10, c, 63u & ~m);
+        }
+    }
+    f.diff *= c.nS;
+    f.bres = 0; f.bav = 0;
+#pragma unroll
+    for (int s = 0; s < 15; s++) {
+        const uint32_t id = s < 12 ? byte_of(e.d[s >> 2], s & 3) : byte_of(c.resv, s - 12);
+        if (id == NONE8) continue;
+        const uint2 cw = T.card[id];
+        uint32_t pay;
+        if (!can_buy(c, cw, pay)) continue;
+        const uint32_t Sb = c.S | ((c.near >> (cw.y & 31u)) & 31u);
+        const int k = Sb ? __popc(Sb) : 1;
+        if (s < 12) f.bav += k; else f.bres += k;
+    }
+    return f.res + f.same + f.diff + f.bres + f.bav;
+}
+
+// k-th legal action in ascending ALL_ACTIONS order (k < total; total == 0 means only passes are legal, k < nS)
+template <int P>
+__device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, const Ctx &c, const FamilyCounts &f,
+                                             int total, int k, Choice &ch)
+{
+    ch.C = 0; ch.R = 0; ch.info = 0; ch.slot = 0;
+    if (total == 0) {  // pass (:570-574)
+        ch.type = T_PASS;
+        ch.n = c.S ? select_bit8(c.S, k) + 1 : 0;
+        ch.idx = ch.n;
+        return;
+    }
+    if (k < f.res) {  // reserve: index 6 + p*42 + n*7 + v
+        const int nv = reserve_variants(c), per = c.nS * nv;
+        const int q = small_div(k, per), rem = k - q * per, ni = small_div(rem, nv), vi = rem - ni * nv;
+        ch.type = T_RESERVE;
+        ch.slot = select_bit(c.occ, q);
+        ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
+        int v = 0;
+        if (c.bank_yellow) {
+            v = 1; ch.C = 1u << YSH;
+            if (c.hold >= 10) {
+                const int fl = select_bit8(c.h1 & NORMAL_FIELDS, vi);
+                v = 2 + fl - (fl > 2 ? 1 : 0);
+                ch.R = 1u << (5 * fl);
+            }
+        }
+        ch.idx = BASE_RESERVE + ch.slot * 42 + ch.n * 7 + v;
+        return;
+    }
+    k -= f.res;
+    if (k < f.same) {  // collect_same: 510 + c*126 + n*21 + v
+        const int e2 = c.hold - 8;
+        int col = 0, nv = 1;
+        for (; col < 5; col++) {
+            const int fl = field_of_normal(col);
+            if (!(c.A4 >> fl & 1)) continue;
+            nv = n_returns(e2, c, 63u & ~(1u << fl));
+            if (k < nv * c.nS) break;
+            k -= nv * c.nS;
+        }
+        const int ni = small_div(k, nv), vi = k - ni * nv;
+        const uint32_t *row = T.ret_same + col * 21;
+        int v = 0;
+        if (e2 == 1) v = nth_feasible(row, 11, 16, vi, c.gems);
+        else if (e2 == 2) {
+            v = nth_feasible(row, 1, 11, vi, c.gems);
+            if (v == 11) {  // fewer than vi+1 feasible pairs: continue among "two of one colour"
+                const int a1 = __popc(c.h1 & 63u & ~(1u << field_of_normal(col)));
+                v = nth_feasible(row, 16, 21, vi - (a1 * (a1 - 1) >> 1), c.gems);
+            }
+        }
+        ch.type = T_SAME; ch.slot = col;
+        ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
+        ch.C = 2u << (5 * field_of_normal(col));
+        ch.R = row[v];
+        ch.idx = BASE_SAME + col * 126 + ch.n * 21 + v;
+        return;
+    }
+    k -= f.same;
+    if (k < f.diff) {  // collect_diff: combo_base + n*V + v
+        int ci, nv = 1, L;
+        if (c.hold <= 7) {
+            const int q = small_div(k, c.nS);
+            k -= q * c.nS;
+            int seen = 0;
+            L = c.Lmax;
+            ci = L == 1 ? 0 : (L == 2 ? 5 : 15);
+            for (; ci < 24; ci++) {
+                if (T.combo_mask[ci] & ~c.A1) continue;
+                if (seen++ == q) break;
+            }
+        } else {
+            for (ci = 0; ci < 25; ci++) {
+                const uint32_t m = T.combo_mask[ci];
+                L = combo_len(ci);
+                if ((m & ~c.A1) || L < c.Lmin) continue;
+                nv = n_returns(c.hold + L - 10, c, 63u & ~m);
+                if (k < nv * c.nS) break;
+                k -= nv * c.nS;
+            }
+        }
+        const int ni = small_div(k, nv), vi = k - ni * nv;
+        const int ex = c.hold + L - 10, kk = 6 - L, V = L == 1 ? 6 : (L == 2 ? 15 : 20);
+        const uint32_t *row = T.ret_diff + T.combo_off[ci];
+        int v = 0;
+        if (ex > 0) {
+            const int r1 = 1 + kk, r2 = r1 + (kk * (kk + 1) >> 1);  // first variant returning 2 / 3 gems
+            v = ex == 1 ? nth_feasible(row, 1, r1, vi, c.gems)
+                        : (ex == 2 ? nth_feasible(row, r1, r2, vi, c.gems) : nth_feasible(row, r2, V, vi, c.gems));
+        }
+        ch.type = T_DIFF; ch.slot = ci;
+        ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
+        ch.C = T.combo_c[ci];
+        ch.R = row[v];
+        ch.idx = T.combo_base[ci] + ch.n * V + v;
+        return;
+    }
+    k -= f.diff;
+    // buys: reserved cards first (3420 + r*6 + n), then the board (3438 + p*6 + n)
+#pragma unroll 1
+    for (int i = 0; i < 15; i++) {
+        const int s = i < 3 ? 12 + i : i - 3;
+        uint32_t w = s < 4 ? e.d[0] : (s < 8 ? e.d[1] : (s < 12 ? e.d[2] : c.resv));
+        const uint32_t id = byte_of(w, s & 3);
+        if (id == NONE8) continue;
+        const uint2 cw = T.card[id];
+        uint32_t pay;
+        if (!can_buy(c, cw, pay)) continue;
+        const uint32_t Sb = c.S | ((c.near >> (cw.y & 31u)) & 31u);
+        const int cnt = Sb ? __popc(Sb) : 1;
+        if (k >= cnt) { k -= cnt; continue; }
+        ch.type = s < 12 ? T_BUY_AVAILABLE : T_BUY_RESERVE;
+        ch.slot = s < 12 ? s : s - 12;
+        ch.n = Sb ? select_bit8(Sb, k) + 1 : 0;
+        ch.R = pay; ch.info = cw.y;
+        ch.idx = (s < 12 ? BASE_BUY_AVAILABLE + s * 6 : BASE_BUY_RESERVE + (s - 12) * 6) + ch.n;
+        return;
+    }
+    ch.type = T_PASS; ch.n = 0; ch.idx = 0;  // unreachable when counts are consistent
+}
+
+// Is ALL_ACTIONS[idx] legal for the seat to move?  Decodes it into ch either way (build_action, gym/envs/utils.py:43-145).
+// This is the membership form of the same rules, written independently of count/select so the two cross-check.
+template <int P>
+__device__ __forceinline__ bool decode_and_check(const Env<P> &e, const Tables &T, const Ctx &c, int idx, Choice &ch)
+{
+    ch.idx = idx; ch.C = 0; ch.R = 0; ch.info = 0; ch.slot = 0; ch.n = 0; ch.type = T_PASS;
+    if (idx < 0 || idx >= SPL_NUM_ACTIONS) return false;
+    bool ok;
+    uint32_t S = c.S;
+    if (idx < BASE_RESERVE) {
+        FamilyCounts f;
+        ch.n = idx;
+        ok = count_legal(e, T, c, f) == 0;
+    } else if (idx < BASE_SAME) {
+        const int r = idx - BASE_RESERVE, p = r / 42, v = r % 7;
+        ch.type = T_RESERVE; ch.slot = p; ch.n = (r % 42) / 7;
+        int expect_lo, expect_hi;
+        if (!c.bank_yellow) expect_lo = expect_hi = 0;
+        else if (c.hold < 10) expect_lo = expect_hi = 1;
+        else { expect_lo = 2; expect_hi = 6; }
+        ok = c.n_resv < 3 && (c.occ >> p & 1) && v >= expect_lo && v <= expect_hi;
+        if (v >= 1) ch.C = 1u << YSH;
+        if (v >= 2) {
+            const int fl = field_of_normal(v - 2);
+            ch.R = 1u << (5 * fl);
+            ok = ok && (c.h1 >> fl & 1);
+        }
+    } else if (idx < BASE_DIFF) {
+        const int r = idx - BASE_SAME, col = r / 126, v = r % 21, fl = field_of_normal(col);
+        ch.type = T_SAME; ch.slot = col; ch.n = (r % 126) / 21;
+        ch.C = 2u << (5 * fl);
+        ch.R = T.ret_same[col * 21 + v];
+        ok = (c.A4 >> fl & 1) && (int)hsum6(ch.R) == max(c.hold - 8, 0) && satsub6(ch.R, c.gems) == 0;
+    } else if (idx < BASE_BUY_RESERVE) {
+        const int r = idx - BASE_DIFF;
+        int ci, rem, V;
+        if (r < 180) { ci = r / 36; rem = r % 36; V = 6; }
+        else if (r < 1080) { ci = 5 + (r - 180) / 90; rem = (r - 180) % 90; V = 15; }
+        else { ci = 15 + (r - 1080) / 120; rem = (r - 1080) % 120; V = 20; }
+        const int L = combo_len(ci), v = rem % V;
+        const uint32_t m = T.combo_mask[ci];
+        ch.type = T_DIFF; ch.slot = ci; ch.n = rem / V;
+        ch.C = T.combo_c[ci];
+        ch.R = T.ret_diff[T.combo_off[ci] + v];
+        ok = !(m & ~c.A1) && L >= c.Lmin && (int)hsum6(ch.R) == max(c.hold + L - 10, 0) && satsub6(ch.R, c.gems) == 0;
+    } else {
+        const bool avail = idx >= BASE_BUY_AVAILABLE;
+        const int r = idx - (avail ? BASE_BUY_AVAILABLE : BASE_BUY_RESERVE), s = r / 6;
+        ch.type = avail ? T_BUY_AVAILABLE : T_BUY_RESERVE; ch.slot = s; ch.n = r % 6;
+        uint32_t w = e.d[0];
+        if ((s >> 2) == 1) w = e.d[1];
+        if ((s >> 2) == 2) w = e.d[2];
+        const uint32_t id = avail ? byte_of(w, s & 3) : byte_of(c.resv, s);
+        ok = id != NONE8;
+        const uint2 cw = T.card[ok ? id : 95];
+        ok = ok && can_buy(c, cw, ch.R);
+        ch.info = cw.y;
+        S |= (c.near >> (cw.y & 31u)) & 31u;
+    }
+    const bool noble_ok = S ? (ch.n >= 1 && (S >> (ch.n - 1) & 1)) : ch.n == 0;
+    return ok && noble_ok;
+}
+
+// ------------------------------------------------------------------------------------------------ successor
+// generateSuccessor + GameRule.update.  Returns the acting agent's score delta.
+template <int P>
+__device__ __forceinline__ int apply_action(Env<P> &e, const Choice &ch, const DeckSrc &src)
+{
+    const int seat = seat_of(e.meta);
+    uint32_t g = e.pg[0], cd = e.pc[0], rv = e.pr[0], pi = e.pi[0];
+#pragma unroll
+    for (int p = 1; p < P; p++)
+        if (seat == p) { g = e.pg[p]; cd = e.pc[p]; rv = e.pr[p]; pi = e.pi[p]; }
+
+    g = g + ch.C - ch.R;
+    e.bank = e.bank - ch.C + ch.R;
+    int score = 0;
+    if (ch.type == T_RESERVE || ch.type == T_BUY_AVAILABLE) {
+        const int tier = ch.slot >> 2, col = ch.slot & 3;
+        uint32_t w = e.d[0];
+        if (tier == 1) w = e.d[1];
+        if (tier == 2) w = e.d[2];
+        const uint32_t id = byte_of(w, col);
+        w = set_byte(w, col, deal(e, tier, src));
+        if (tier == 0) e.d[0] = w; else if (tier == 1) e.d[1] = w; else e.d[2] = w;
+        if (ch.type == T_RESERVE) rv = set_byte(rv, __popc(~rv & 0x00808080u), id);
+    } else if (ch.type == T_BUY_RESERVE) {
+        const uint32_t list = rv & 0x00FFFFFFu, sh = 8u * ch.slot;
+        rv = (rv & 0xFF000000u) | (list & ((1u << sh) - 1u)) | ((list >> (sh + 8u)) << sh) | 0x00FF0000u;
+    }
+    if (ch.type >= T_BUY_RESERVE) {
+        cd += 1u << (ch.info & 31u);
+        score += (int)((ch.info >> 5) & 7u);
+    }
+    if (ch.n > 0) {  // the noble leaves the board list; later nobles shift down (:280-289)
+        const uint32_t list = e.meta & 0xFFFFFu, sh = 4u * (ch.n - 1);
+        const uint32_t id = (list >> sh) & 15u;
+        e.meta = (e.meta & ~0xFFFFFu) | (list & ((1u << sh) - 1u)) | ((list >> (sh + 4u)) << sh) | 0xF0000u;
+        pi |= 1u << (16 + id);
+        score += 3;
+    }
+    rv += (uint32_t)score << 24;
+    pi = ((pi + 1u) & ~(1u << 26)) | (ch.type == T_PASS ? 1u << 26 : 0u);
+#pragma unroll
+    for (int p = 0; p < P; p++)
+        if (seat == p) { e.pg[p] = g; e.pc[p] = cd; e.pr[p] = rv; e.pi[p] = pi; }
+    const int next = seat + 1 == P ? 0 : seat + 1;
+    e.meta = (e.meta & ~(3u << 20)) | ((uint32_t)next << 20);
+    return score;
+}
+
+template <int P>
+__device__ __forceinline__ int game_ends(const Env<P> &e, uint32_t flags)
+{
+    bool all100 = true, all_passed = true, any15 = false;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        all100 = all100 && (e.pi[p] & 0xFFFFu) == 100u;
+        all_passed = all_passed && (e.pi[p] >> 26 & 1u);
+        any15 = any15 || (e.pr[p] >> 24) >= 15u;
+    }
+    if ((flags & SPL_F_LIMIT_ROUNDS) && all100) return SPL_END_ROUNDCAP;
+    if (any15 && seat_of(e.meta) == 0) return SPL_END_SCORE;
+    return all_passed ? SPL_END_DEADLOCK : SPL_END_NONE;
+}
+
+// calScore x 2 for every seat (+1 = the half point, :308-323) and win(2)/tie(1)/loss(0)
+template <int P>
+__device__ __forceinline__ void final_scores(const Env<P> &e, int (&score2)[P], int (&outcome)[P])
+{
+    int sc[P], bought[P], mx = 0, min_cards = 1 << 20, victors = 0;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        sc[p] = (int)(e.pr[p] >> 24);
+        bought[p] = (int)hsum6(e.pc[p]);
+        mx = max(mx, sc[p]);
+        min_cards = min(min_cards, bought[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < P; p++) victors += sc[p] == mx;
+    int best = -1, nbest = 0;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        score2[p] = 2 * sc[p] + ((victors > 1 && sc[p] == mx && bought[p] == min_cards) ? 1 : 0);
+        best = max(best, score2[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < P; p++) nbest += score2[p] == best;
+#pragma unroll
+    for (int p = 0; p < P; p++) outcome[p] = score2[p] == best ? (nbest > 1 ? 1 : 2) : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ warp-per-env pieces
+// The legal-action MASK and the OBSERVATION are produced by one warp per env; these are the per-lane bodies (the
+// kernels add the warp synchronisation, the ballot for "nothing legal -> pass" and the coalesced stores).
+constexpr int MASK_PAD = 112;
+constexpr int OBS_PAD = 272;
+
+__device__ __forceinline__ void set_bit(uint32_t *m, int idx) { atomicOr(&m[idx >> 5], 1u << (idx & 31)); }
+
+// Sets one bit per noble slot: base + n*stride for n in (S ? {k+1 : k in S} : {0})
+__device__ __forceinline__ void set_for_nobles(uint32_t *m, int base, int stride, uint32_t S)
+{
+    if (S == 0) { set_bit(m, base); return; }
+    for (uint32_t s = S; s; s &= s - 1) set_bit(m, base + __ffs(s) * stride);
+}
+
+// Lane `lane` of the warp that owns env e sets its share of the 3510 mask bits in m (zeroed, >= 110 words, shared
+// memory).  Returns whether it set anything; if no lane did, the caller sets the pass bits (set_for_nobles(m,0,1,S)).
+template <int P>
+__device__ __forceinline__ bool lane_fill_mask(const Env<P> &e, const Tables &T, const Ctx &c, uint32_t *m, int lane)
+{
+    bool any = false;
+    // reserve: lane = board slot (:498-520)
+    if (lane < 12 && c.n_resv < 3 && (c.occ >> lane & 1)) {
+        const int base = BASE_RESERVE + lane * 42;
+        if (!c.bank_yellow) set_for_nobles(m, base, 7, c.S);
+        else if (c.hold < 10) set_for_nobles(m, base + 1, 7, c.S);
+        else
+            for (int n = 0; n < 5; n++)
+                if (c.h1 >> field_of_normal(n) & 1) set_for_nobles(m, base + 2 + n, 7, c.S);
+        any = true;
+    }
+    // collect_same: lanes 12..16 = colour (:475-496)
+    if (lane >= 12 && lane < 17) {
+        const int col = lane - 12, fl = field_of_normal(col), e2 = c.hold - 8;
+        if (c.A4 >> fl & 1) {
+            const uint32_t *row = T.ret_same + col * 21;
+            const int base = BASE_SAME + col * 126;
+            if (e2 <= 0) { set_for_nobles(m, base, 21, c.S); any = true; }
+            else
+                for (int v = 1; v < 21; v++)
+                    if ((int)hsum6(row[v]) == e2 && satsub6(row[v], c.gems) == 0) { set_for_nobles(m, base + v, 21, c.S); any = true; }
+        }
+    }
+    // collect_diff: lane = colour combination (:437-473)
+    if (lane < 25) {
+        const int L = combo_len(lane), V = L == 1 ? 6 : (L == 2 ? 15 : 20), ex = c.hold + L - 10;
+        if (!(T.combo_mask[lane] & ~c.A1) && L >= c.Lmin) {
+            const uint32_t *row = T.ret_diff + T.combo_off[lane];
+            const int base = T.combo_base[lane];
+            if (ex <= 0) { set_for_nobles(m, base, V, c.S); any = true; }
+            else
+                for (int v = 1; v < V; v++)
+                    if ((int)hsum6(row[v]) == ex && satsub6(row[v], c.gems) == 0) { set_for_nobles(m, base + v, V, c.S); any = true; }
+        }
+    }
+    // buy: lanes 17..31 = 12 board slots + 3 reserved cards (:522-568)
+    if (lane >= 17) {
+        const int s = lane - 17;
+        uint32_t w = s < 4 ? e.d[0] : (s < 8 ? e.d[1] : (s < 12 ? e.d[2] : c.resv));
+        const uint32_t id = byte_of(w, s & 3);
+        uint32_t pay;
+        if (id != NONE8) {
+            const uint2 cw = T.card[id];
+            if (can_buy(c, cw, pay)) {
+                const uint32_t Sb = c.S | ((c.near >> (cw.y & 31u)) & 31u);
+                set_for_nobles(m, s < 12 ? BASE_BUY_AVAILABLE + s * 6 : BASE_BUY_RESERVE + (s - 12) * 6, 1, Sb);
+                any = true;
+            }
+        }
+    }
+    return any;
+}
+
+// features.extract_metrics_with_cards (features.py:214-310, :377-480) for `seat`, into o[0..264] (zeroed, shared memory).
+// Phase A: lanes 0..14 own one card each (12 board slots, then the 3 reserved slots) and publish (distance, colour)
+// in scratch[0..14]; the warp synchronises; phase B: lanes 16..20 own one board noble each, lane 24 the scalar metrics.
+template <int P>
+__device__ __forceinline__ void lane_fill_obs_cards(const Env<P> &e, const Tables &T, int seat, float *o, uint32_t *scratch, int lane)
+{
+    if (lane >= 15) return;
+    uint32_t gems = e.pg[0], cards = e.pc[0], resv = e.pr[0];
+#pragma unroll
+    for (int p = 1; p < P; p++)
+        if (seat == p) { gems = e.pg[p]; cards = e.pc[p]; resv = e.pr[p]; }
+    const uint32_t bp = (gems & ~(31u << YSH)) + cards;  // buying power per normal colour (features.py:65-74), <= 14
+    const int s = lane;
+    const uint32_t w = s < 4 ? e.d[0] : (s < 8 ? e.d[1] : (s < 12 ? e.d[2] : resv));
+    const uint32_t id = byte_of(w, s & 3);
+    uint32_t dist = 0, colour_shift = 31;  // 5*field of the card's colour, 31 = no card here
+    if (id != NONE8) {
+        const uint2 cw = T.card[id];
+        const uint32_t miss = satsub6(cw.x, bp);
+        const uint32_t sum = hsum6(miss);
+        uint32_t mx = 0;
+#pragma unroll
+        for (int f = 0; f < 6; f++) mx = max(mx, field(miss, 5 * f));
+        const uint32_t turns = sum == 0 ? 0u : max((sum + 2u) / 3u, mx);  // features.py:124-135
+        dist = sum; colour_shift = cw.y & 31u;
+        o[(s < 12 ? 30 : 54 - 12) + s] = (float)sum;
+        o[(s < 12 ? 42 : 57 - 12) + s] = (float)turns;
+        // vectorize_card (features.py:377-413): one-hot over sklearn's alphabetical categories black, blue, green, red,
+        // white, yellow; then the cost in alphabetical order black, blue, green, red, white; deck_id; points
+        float *v = o + 70 + 13 * s;
+        const int fld = (int)(colour_shift / 5u);  // 0 black 1 red 3 green 4 blue 5 white
+        v[fld == 0 ? 0 : (fld == 1 ? 3 : (fld == 3 ? 2 : (fld == 4 ? 1 : 4)))] = 1.f;
+        v[6] = (float)field(cw.x, 0);
+        v[7] = (float)field(cw.x, 20);
+        v[8] = (float)field(cw.x, 15);
+        v[9] = (float)field(cw.x, 5);
+        v[10] = (float)field(cw.x, 25);
+        v[11] = (float)(cw.y >> 8 & 3u);
+        v[12] = (float)(cw.y >> 5 & 7u);
+    }
+    scratch[s] = dist | colour_shift << 8;
+}
+
+template <int P>
+__device__ __forceinline__ void lane_fill_obs_rest(const Env<P> &e, const Tables &T, const uint32_t *log1p_bits, int seat,
+                                                   float *o, const uint32_t *scratch, int lane)
+{
+    uint32_t gems = e.pg[0], cards = e.pc[0], resv = e.pr[0], pinfo = e.pi[0];
+#pragma unroll
+    for (int p = 1; p < P; p++)
+        if (seat == p) { gems = e.pg[p]; cards = e.pc[p]; resv = e.pr[p]; pinfo = e.pi[p]; }
+    if (lane >= 16 && lane < 21) {  // distance to one board noble (features.py:257-274)
+        const int k = lane - 16;
+        const uint32_t id = (e.meta >> (4 * k)) & 15u;
+        if (id != 15u) {
+            const uint32_t missing = satsub6(T.noble[id], cards);
+            int dist_gems = 0;
+            uint32_t used = 0;
+            for (int f = 0; f < 6; f++) {
+                const int cnt = (int)field(missing, 5 * f);
+                for (int it = 0; it < cnt; it++) {  // the cnt cheapest candidate cards of this colour, 14 per absent one
+                    int best = 255, bj = -1;
+                    for (int j = 0; j < 15; j++) {
+                        const uint32_t sj = scratch[j];
+                        if ((sj >> 8) == (uint32_t)(5 * f) && !(used >> j & 1) && (int)(sj & 0xFFu) < best) {
+                            best = (int)(sj & 0xFFu); bj = j;
+                        }
+                    }
+                    if (bj >= 0) used |= 1u << bj;
+                    dist_gems += bj >= 0 ? best : 14;
+                }
+            }
+            o[60 + k] = (float)dist_gems;
+            o[65 + k] = (float)hsum6(missing);
+        }
+    }
+    if (lane == 24) {  // the scalar metrics (features.py:284-299)
+        const uint32_t bp = (gems & ~(31u << YSH)) + cards;
+        const uint32_t score = resv >> 24;
+        o[0] = 1.f;
+        o[1] = (float)(pinfo & 0xFFFFu);
+        o[2] = (float)score;
+        o[3] = score >= 15u ? 1.f : 0.f;
+        o[4] = (float)hsum6(cards);
+        o[5] = (float)__popc(~resv & 0x00808080u);
+        int s1 = 0, s2 = 0;
+#pragma unroll
+        for (int n = 0; n < 5; n++) {
+            const int sh = 5 * field_of_normal(n);
+            const int b = (int)field(bp, sh);
+            s1 += b; s2 += b * b;
+            o[9 + n] = (float)field(cards, sh);
+            o[14 + n] = (float)b;
+            o[19 + n] = __uint_as_float(log1p_bits[b]);
+        }
+        // np.var of five small integers = (5*sum(x^2) - sum(x)^2) / 25; numerator < 2^24, IEEE division: exact rounding
+        o[6] = __fdiv_rn((float)(5 * s2 - s1 * s1), 25.0f);
+        o[7] = (float)field(gems, YSH);
+        o[8] = (float)hsum6(gems);
+#pragma unroll
+        for (int p = 0; p < P; p++) {  // features.py:276-282, its i-1 indexing quirk kept
+            const float sc = (float)(e.pr[p] >> 24);
+            if (p < seat) o[24 + p] = sc;
+            else if (p > seat) o[27 + p - 1] = sc;
+        }
+    }
+}
+
+}  // namespace spl

@@ -1,0 +1,617 @@
+// kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/splendor_b200.h.
+//
+//   playout_kernel      thread-per-game, state in registers for the whole game: reset -> {terminal test, legal count,
+//                       Philox choice, k-th legal action, apply} x steps -> calScore -> counters.  No HBM traffic inside
+//                       the loop except the optional trace.
+//   legal_mask_kernel   warp-per-env: lanes own board slots / colours / colour combinations / cards, set bits of the
+//                       3510-bit mask in shared memory, and the warp writes the 110 words coalesced.
+//   step_kernel         thread-per-env: decode the ALL_ACTIONS index, membership test, apply, reward / done / illegal.
+//   observe_kernel      warp-per-env: 265-float observation assembled in shared memory, coalesced store.
+//   env_step_kernel     thread-per-env learner move + in-kernel random opponents, then warp-per-env mask + observation
+//                       out of shared memory (the PPO rollout call).
+//   reset / inject / final_scores: thread-per-env.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <mutex>
+
+#include "engine.cuh"
+
+namespace spl {
+
+__device__ const Tables g_tables = make_tables();
+__device__ const uint32_t g_log1p_bits[32] = SPL_LOG1P_BITS;
+
+constexpr int BLOCK = 128;
+
+__device__ __forceinline__ void stage_tables(Tables &sT)
+{
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&g_tables);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&sT);
+    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+static_assert(sizeof(Tables) % 4 == 0, "Tables must be word-copyable");
+
+// ---------------------------------------------------------------------------------------------- reset / inject
+template <int P>
+__global__ void __launch_bounds__(BLOCK) reset_kernel(uint4 *state, uint64_t seed, uint64_t first_game, int64_t N,
+                                                      uint8_t *deck_lists_out, uint8_t *nobles_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Env<P> e;
+    const uint64_t game = first_game + (uint64_t)i;
+    reset_env(e, seed, game);
+    store_env(e, state, N, i);
+    if (nobles_out)
+        for (int k = 0; k < 5; k++) {
+            const uint32_t id = (e.meta >> (4 * k)) & 15u;
+            nobles_out[i * 5 + k] = id == 15u ? 0xFF : (uint8_t)id;
+        }
+    if (deck_lists_out) {  // finish drawing every deck so the whole order can be handed to the reference engine
+        uint8_t *out = deck_lists_out + i * SPL_DECK_BYTES;
+        const DeckSrc src{nullptr, seed, game};
+        for (int t = 0; t < 3; t++) {
+            const int size = t == 0 ? 40 : (t == 1 ? 30 : 20), base = t == 0 ? 0 : (t == 1 ? 40 : 70);
+            for (int c = 0; c < 4; c++) out[base + size - 1 - c] = (uint8_t)byte_of(e.d[t], c);
+            for (int d = 4; d < size; d++) out[base + size - 1 - d] = (uint8_t)deal(e, t, src);
+        }
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(BLOCK) inject_kernel(uint4 *state, const uint8_t *deck_lists, const uint8_t *nobles, int64_t N)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Env<P> e;
+    const uint32_t n = P == 2 ? 4 : (P == 3 ? 5 : 7);
+    e.bank = n * (ONES6 & ~(1u << YSH)) | (5u << YSH);
+    e.k[0] = 40u | 30u << 8 | 20u << 16; e.k[1] = 0; e.k[2] = 0;
+    uint32_t list = 0xFFFFFu;
+    for (int k = 0; k < P + 1; k++) list = (list & ~(15u << (4 * k))) | ((uint32_t)(nobles[i * 5 + k] & 15u) << (4 * k));
+    e.meta = list | ((uint32_t)(P - 2) << 22) | META_EXPLICIT;
+    const DeckSrc src{deck_lists + i * SPL_DECK_BYTES, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) w |= deal(e, t, src) << (8 * c);
+        e.d[t] = w;
+    }
+#pragma unroll
+    for (int p = 0; p < P; p++) { e.pg[p] = 0; e.pc[p] = 0; e.pr[p] = 0x00FFFFFFu; e.pi[p] = 0; }
+    store_env(e, state, N, i);
+}
+
+// ---------------------------------------------------------------------------------------------- playout
+struct PlayoutArgs {
+    uint4 *state;           // FRESH: optional final-state output; else in/out states
+    const uint8_t *decks;   // explicit deck lists (only with states) or nullptr
+    uint64_t seed, first_game;
+    int64_t n_games;
+    uint32_t flags;
+    int max_steps;
+    int8_t *score2;
+    int16_t *steps;
+    uint8_t *end_kind;
+    unsigned long long *counters;
+    int16_t *trace;
+    int trace_len;
+};
+
+template <int P>
+__device__ __forceinline__ uint32_t turns_total(const Env<P> &e)
+{
+    uint32_t t = 0;
+#pragma unroll
+    for (int p = 0; p < P; p++) t += e.pi[p] & 0xFFFFu;
+    return t;
+}
+
+template <int P, bool FRESH>
+__global__ void __launch_bounds__(BLOCK) playout_kernel(const PlayoutArgs a)
+{
+    __shared__ Tables sT;
+    __shared__ unsigned long long sctr[16];
+    if (threadIdx.x < 16) sctr[threadIdx.x] = 0;
+    stage_tables(sT);
+
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool done = g >= a.n_games, have = false;
+    Env<P> e;
+    int t = 0, t_end = 0;
+    DeckSrc src{nullptr, a.seed, 0};
+
+    while (!__all_sync(0xFFFFFFFFu, done)) {
+        if (!done) {
+            if (!have) {  // next game of this lane
+                src.game = a.first_game + (uint64_t)g;
+                if (FRESH) reset_env(e, a.seed, src.game);
+                else {
+                    load_env(e, a.state, a.n_games, g);
+                    src.lists = a.decks ? a.decks + g * SPL_DECK_BYTES : nullptr;
+                }
+                t = (int)turns_total(e);
+                t_end = t + a.max_steps;
+                have = true;
+            }
+            int kind = game_ends(e, a.flags);
+            if (kind == SPL_END_NONE && t >= t_end) kind = SPL_END_TRUNCATED;
+            if (kind == SPL_END_NONE) {
+                Ctx c;
+                FamilyCounts f;
+                Choice ch;
+                make_ctx(e, sT, c);
+                const int total = count_legal(e, sT, c, f);
+                const uint32_t r = philox(a.seed, src.game, (uint32_t)t, STREAM_ACTION).x;
+                select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
+                if (a.trace && t < a.trace_len) a.trace[(int64_t)t * a.n_games + g] = (int16_t)ch.idx;
+                apply_action(e, ch, src);
+                t++;
+            } else {  // game over: calScore, win/tie/loss, counters, outputs
+                int sc[P], oc[P];
+                final_scores(e, sc, oc);
+                unsigned long long nob = 0, sum = 0;
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    if (a.score2) a.score2[g * P + p] = (int8_t)sc[p];
+                    if (oc[p] == 2) atomicAdd(&sctr[SPL_CTR_WINS + p], 1ull);
+                    if (oc[p] == 1) atomicAdd(&sctr[SPL_CTR_TIES + p], 1ull);
+                    sum += (unsigned)sc[p];
+                    nob += __popc(e.pi[p] >> 16 & 0x3FFu);
+                }
+                atomicAdd(&sctr[SPL_CTR_GAMES], 1ull);
+                atomicAdd(&sctr[SPL_CTR_STEPS], (unsigned long long)t);
+                atomicAdd(&sctr[SPL_CTR_END_SCORE - 1 + kind], 1ull);
+                atomicAdd(&sctr[SPL_CTR_SCORE2_SUM], sum);
+                atomicAdd(&sctr[SPL_CTR_NOBLES], nob);
+                if (a.steps) a.steps[g] = (int16_t)t;
+                if (a.end_kind) a.end_kind[g] = (uint8_t)kind;
+                if (a.state) store_env(e, a.state, a.n_games, g);
+                have = false;
+                g += stride;
+                done = g >= a.n_games;
+            }
+        }
+    }
+    __syncthreads();
+    if (a.counters && threadIdx.x < 16 && sctr[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], sctr[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------- step
+template <int P>
+__global__ void __launch_bounds__(BLOCK) step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+                                                     const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal,
+                                                     int64_t N, uint32_t flags)
+{
+    __shared__ Tables sT;
+    stage_tables(sT);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int a = action[i];
+    Env<P> e;
+    load_env(e, state, N, i);
+    int rew = 0, bad = 0;
+    if (a >= 0) {
+        Ctx c;
+        Choice ch;
+        make_ctx(e, sT, c);
+        if (decode_and_check(e, sT, c, a, ch)) {
+            const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, first_game + (uint64_t)i};
+            rew = apply_action(e, ch, src);
+        } else {
+            bad = 1;
+            e.meta |= META_ILLEGAL;
+        }
+        store_env(e, state, N, i);
+    }
+    if (reward) reward[i] = (int8_t)rew;
+    if (illegal) illegal[i] = (uint8_t)bad;
+    if (done) done[i] = (uint8_t)game_ends(e, flags);
+}
+
+template <int P>
+__global__ void __launch_bounds__(BLOCK) final_scores_kernel(const uint4 *state, int8_t *score2, uint8_t *outcome,
+                                                             uint8_t *end_kind, int64_t N, uint32_t flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Env<P> e;
+    load_env(e, state, N, i);
+    int sc[P], oc[P];
+    final_scores(e, sc, oc);
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        if (score2) score2[i * P + p] = (int8_t)sc[p];
+        if (outcome) outcome[i * P + p] = (uint8_t)oc[p];
+    }
+    if (end_kind) end_kind[i] = (uint8_t)game_ends(e, flags);
+}
+
+// ---------------------------------------------------------------------------------------------- legal mask (warp per env)
+template <int P>
+__global__ void __launch_bounds__(BLOCK) legal_mask_kernel(const uint4 *state, uint32_t *mask, int64_t N)
+{
+    __shared__ Tables sT;
+    __shared__ uint32_t sm[BLOCK / 32][MASK_PAD];
+    stage_tables(sT);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    uint32_t *m = sm[warp];
+    for (int64_t i = (int64_t)blockIdx.x * (BLOCK / 32) + warp; i < N; i += nwarps) {
+        for (int w = lane; w < MASK_PAD; w += 32) m[w] = 0;
+        Env<P> e;
+        load_env(e, state, N, i);  // same address in every lane: one broadcast transaction per chunk
+        Ctx c;
+        make_ctx(e, sT, c);
+        __syncwarp();
+        const bool any = lane_fill_mask(e, sT, c, m, lane);
+        if (__ballot_sync(0xFFFFFFFFu, any) == 0 && lane == 0) set_for_nobles(m, 0, 1, c.S);  // pass (:570-574)
+        __syncwarp();
+        uint32_t *out = mask + i * SPL_MASK_WORDS;
+        for (int w = lane; w < SPL_MASK_WORDS; w += 32) out[w] = m[w];
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- observation (warp per env)
+template <int P>
+__global__ void __launch_bounds__(BLOCK) observe_kernel(const uint4 *state, const int8_t *seat, float *obs, int64_t N)
+{
+    __shared__ Tables sT;
+    __shared__ float so[BLOCK / 32][OBS_PAD];
+    __shared__ uint32_t sscr[BLOCK / 32][16];
+    stage_tables(sT);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    for (int64_t i = (int64_t)blockIdx.x * (BLOCK / 32) + warp; i < N; i += nwarps) {
+        Env<P> e;
+        load_env(e, state, N, i);
+        const int s = seat ? (int)seat[i] : seat_of(e.meta);
+        for (int w = lane; w < OBS_PAD; w += 32) so[warp][w] = 0.f;
+        __syncwarp();
+        lane_fill_obs_cards(e, sT, s, so[warp], sscr[warp], lane);
+        __syncwarp();
+        lane_fill_obs_rest(e, sT, g_log1p_bits, s, so[warp], sscr[warp], lane);
+        __syncwarp();
+        float *out = obs + i * SPL_OBS_SIZE;
+        for (int w = lane; w < SPL_OBS_SIZE; w += 32) out[w] = so[warp][w];
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- PPO env step
+// Phase 1 (thread per env): the learner's action, then RandomAgent opponents until the learner's seat or the end.
+// Phase 2 (warp per env, state handed over through shared memory): the learner's next mask and observation.
+template <int P>
+__global__ void __launch_bounds__(BLOCK) env_step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+                                                         const int8_t *learner, const int16_t *action, int8_t *reward,
+                                                         uint8_t *terminated, uint8_t *illegal, uint32_t *mask, float *obs,
+                                                         int64_t N, uint32_t flags)
+{
+    __shared__ Tables sT;
+    __shared__ uint4 sst[2 + P][BLOCK];
+    __shared__ uint32_t sm[BLOCK / 32][MASK_PAD];
+    __shared__ float so[BLOCK / 32][OBS_PAD];
+    __shared__ uint32_t sscr[BLOCK / 32][16];
+    __shared__ int8_t sseat[BLOCK];
+    stage_tables(sT);
+    const int64_t base = (int64_t)blockIdx.x * BLOCK, i = base + threadIdx.x;
+    if (i < N) {
+        Env<P> e;
+        load_env(e, state, N, i);
+        const int me = learner[i], a = action[i];
+        const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, first_game + (uint64_t)i};
+        int rew = 0, bad = 0;
+        bool go = true;
+        if (a >= 0) {
+            Ctx c;
+            Choice ch;
+            make_ctx(e, sT, c);
+            if (seat_of(e.meta) == me && game_ends(e, flags) == SPL_END_NONE && decode_and_check(e, sT, c, a, ch))
+                rew = apply_action(e, ch, src);
+            else { bad = 1; go = false; e.meta |= META_ILLEGAL; }
+        }
+        // _simulate_opponents (splendor_env.py:219-231)
+        for (int guard = 0; go && guard < 4; guard++) {
+            if (seat_of(e.meta) == me || game_ends(e, flags) != SPL_END_NONE) break;
+            Ctx c;
+            FamilyCounts f;
+            Choice ch;
+            make_ctx(e, sT, c);
+            const int total = count_legal(e, sT, c, f);
+            const uint32_t r = philox(seed, src.game, turns_total(e), STREAM_ACTION).x;
+            select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
+            apply_action(e, ch, src);
+        }
+        store_env(e, state, N, i);
+        if (reward) reward[i] = (int8_t)rew;
+        if (illegal) illegal[i] = (uint8_t)bad;
+        if (terminated) terminated[i] = (uint8_t)game_ends(e, flags);
+        sst[0][threadIdx.x] = make_uint4(e.bank, e.d[0], e.d[1], e.d[2]);
+        sst[1][threadIdx.x] = make_uint4(e.k[0], e.k[1], e.k[2], e.meta);
+#pragma unroll
+        for (int p = 0; p < P; p++) sst[2 + p][threadIdx.x] = make_uint4(e.pg[p], e.pc[p], e.pr[p], e.pi[p]);
+        sseat[threadIdx.x] = (int8_t)me;
+    }
+    __syncthreads();
+    if (!mask && !obs) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < BLOCK && base + j < N; j += BLOCK / 32) {
+        Env<P> e;
+        load_env(e, &sst[0][0], BLOCK, j);
+        const int me = sseat[j];
+        // the mask/observation are the LEARNER's (get_legal_actions_mask / _vectorize use my_turn, splendor_env.py:184,206)
+        Env<P> el = e;
+        el.meta = (e.meta & ~(3u << 20)) | ((uint32_t)me << 20);
+        if (mask) {
+            for (int w = lane; w < MASK_PAD; w += 32) sm[warp][w] = 0;
+            Ctx c;
+            make_ctx(el, sT, c);
+            __syncwarp();
+            const bool any = lane_fill_mask(el, sT, c, sm[warp], lane);
+            if (__ballot_sync(0xFFFFFFFFu, any) == 0 && lane == 0) set_for_nobles(sm[warp], 0, 1, c.S);
+            __syncwarp();
+            uint32_t *out = mask + (base + j) * SPL_MASK_WORDS;
+            for (int w = lane; w < SPL_MASK_WORDS; w += 32) out[w] = sm[warp][w];
+        }
+        if (obs) {
+            for (int w = lane; w < OBS_PAD; w += 32) so[warp][w] = 0.f;
+            __syncwarp();
+            lane_fill_obs_cards(e, sT, me, so[warp], sscr[warp], lane);
+            __syncwarp();
+            lane_fill_obs_rest(e, sT, g_log1p_bits, me, so[warp], sscr[warp], lane);
+            __syncwarp();
+            float *out = obs + (base + j) * SPL_OBS_SIZE;
+            for (int w = lane; w < SPL_OBS_SIZE; w += 32) out[w] = so[warp][w];
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace spl
+
+// ================================================================================================ C ABI
+using namespace spl;
+
+static thread_local int g_last_cuda_error = 0;
+#define CK(call)                                   \
+    do {                                           \
+        cudaError_t err__ = (call);                \
+        if (err__ != cudaSuccess) {                \
+            g_last_cuda_error = (int)err__;        \
+            return SPL_E_CUDA;                     \
+        }                                          \
+    } while (0)
+
+static int check_device()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return SPL_E_NODEVICE;
+    return SPL_OK;
+}
+static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+static int sm_count()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+#define DISPATCH_P(P, ...)             \
+    switch (P) {                       \
+    case 2: { constexpr int PP = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int PP = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int PP = 4; __VA_ARGS__; } break; \
+    default: return SPL_E_BADARG;      \
+    }
+
+extern "C" {
+
+int spl_abi_version(void) { return 1; }
+int spl_state_words(int P) { return (P < 2 || P > 4) ? SPL_E_BADARG : 8 + 4 * P; }
+int spl_last_cuda_error(void) { return g_last_cuda_error; }
+const char *spl_error_string(int code)
+{
+    switch (code) {
+    case SPL_OK: return "ok";
+    case SPL_E_BADARG: return "bad argument";
+    case SPL_E_CUDA: return cudaGetErrorString((cudaError_t)g_last_cuda_error);
+    case SPL_E_NODEVICE: return "no CUDA device (this engine has no CPU fallback)";
+    case SPL_E_RANGE: return "max_steps / trace_len out of range";
+    default: return "unknown error";
+    }
+}
+
+int spl_warmup(void)
+{
+    if (int rc = check_device()) return rc;
+    CK(cudaFree(0));
+    sm_count();
+    return SPL_OK;
+}
+
+int spl_reset(void *state, uint64_t seed, uint64_t first_game, int64_t N, int P, uint8_t *deck_lists_out,
+              uint8_t *nobles_out, void *stream)
+{
+    if (!state || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    DISPATCH_P(P, reset_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
+                      (uint4 *)state, seed, first_game, N, deck_lists_out, nobles_out));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_inject(void *state, const uint8_t *deck_lists, const uint8_t *nobles, int64_t N, int P, void *stream)
+{
+    if (!state || !deck_lists || !nobles || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    DISPATCH_P(P, inject_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>((uint4 *)state, deck_lists, nobles, N));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_legal_mask(const void *state, uint32_t *mask, int64_t N, int P, void *stream)
+{
+    if (!state || !mask || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    const int64_t want = (N + BLOCK / 32 - 1) / (BLOCK / 32), cap = (int64_t)sm_count() * 16;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    DISPATCH_P(P, legal_mask_kernel<PP><<<grid, BLOCK, 0, (cudaStream_t)stream>>>((const uint4 *)state, mask, N));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const int16_t *action, int8_t *reward,
+             uint8_t *done, uint8_t *illegal, int64_t N, int P, uint32_t flags, void *stream)
+{
+    if (!state || !action || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    DISPATCH_P(P, step_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
+                      (uint4 *)state, decks, seed, first_game, action, reward, done, illegal, N, flags));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_final_scores(const void *state, int8_t *score2, uint8_t *outcome, uint8_t *end_kind, int64_t N, int P,
+                     uint32_t flags, void *stream)
+{
+    if (!state || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    DISPATCH_P(P, final_scores_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
+                      (const uint4 *)state, score2, outcome, end_kind, N, flags));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_observe(const void *state, const int8_t *seat, float *obs, int64_t N, int P, void *stream)
+{
+    if (!state || !obs || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    const int64_t want = (N + BLOCK / 32 - 1) / (BLOCK / 32), cap = (int64_t)sm_count() * 16;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    DISPATCH_P(P, observe_kernel<PP><<<grid, BLOCK, 0, (cudaStream_t)stream>>>((const uint4 *)state, seat, obs, N));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+static int launch_playout(bool fresh, const PlayoutArgs &a, int P, cudaStream_t stream)
+{
+    if (a.max_steps < 1 || a.max_steps > 4096 || a.trace_len < 0) return SPL_E_RANGE;
+    if (a.trace && a.trace_len > 0)
+        CK(cudaMemsetAsync(a.trace, 0xFF, (size_t)a.trace_len * (size_t)a.n_games * sizeof(int16_t), stream));
+    const int64_t want = (a.n_games + BLOCK - 1) / BLOCK, cap = (int64_t)sm_count() * 8;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (fresh) { DISPATCH_P(P, playout_kernel<PP, true><<<grid, BLOCK, 0, stream>>>(a)); }
+    else { DISPATCH_P(P, playout_kernel<PP, false><<<grid, BLOCK, 0, stream>>>(a)); }
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_playout(uint64_t seed, uint64_t first_game, int64_t num_games, int P, uint32_t flags, int max_steps, int8_t *score2,
+                int16_t *steps, uint8_t *end_kind, int64_t *counters, int16_t *trace, int trace_len, void *final_state,
+                void *stream)
+{
+    if (num_games < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (num_games == 0) return SPL_OK;
+    PlayoutArgs a{(uint4 *)final_state, nullptr, seed, first_game, num_games, flags, max_steps, score2, steps, end_kind,
+                  (unsigned long long *)counters, trace, trace_len};
+    return launch_playout(true, a, P, (cudaStream_t)stream);
+}
+
+int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, int64_t N, int P, uint32_t flags,
+                     int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind, int64_t *counters, int16_t *trace,
+                     int trace_len, void *stream)
+{
+    if (!state || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    PlayoutArgs a{(uint4 *)state, decks, seed, first_game, N, flags, max_steps, score2, steps, end_kind,
+                  (unsigned long long *)counters, trace, trace_len};
+    return launch_playout(false, a, P, (cudaStream_t)stream);
+}
+
+int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const int8_t *learner,
+                 const int16_t *action, int8_t *reward, uint8_t *terminated, uint8_t *illegal, uint32_t *mask, float *obs,
+                 int64_t N, int P, uint32_t flags, void *stream)
+{
+    if (!state || !learner || !action || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    DISPATCH_P(P, env_step_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
+                      (uint4 *)state, decks, seed, first_game, learner, action, reward, terminated, illegal, mask, obs, N, flags));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+// ---- host-buffer path: library-owned, grow-only device staging
+namespace {
+struct Staging {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return SPL_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return SPL_OK;
+    }
+};
+std::mutex g_stage_mu;
+Staging g_stage;
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+}  // namespace
+
+int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t seed, uint64_t first_game, int64_t N, int P,
+                     uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind, int64_t *counters,
+                     void *stream_)
+{
+    if (!deck_lists || !nobles || N < 0 || P < 2 || P > 4) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    const size_t o_state = 0, o_decks = o_state + align256((size_t)N * (8 + 4 * P) * 4),
+                 o_nobles = o_decks + align256((size_t)N * SPL_DECK_BYTES), o_score = o_nobles + align256((size_t)N * 5),
+                 o_steps = o_score + align256((size_t)N * P), o_kind = o_steps + align256((size_t)N * 2),
+                 o_ctr = o_kind + align256((size_t)N), total = o_ctr + 256;
+    if (int rc = g_stage.ensure(total)) return rc;
+    char *b = (char *)g_stage.p;
+    CK(cudaMemcpyAsync(b + o_decks, deck_lists, (size_t)N * SPL_DECK_BYTES, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(b + o_nobles, nobles, (size_t)N * 5, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(b + o_ctr, 0, 128, stream));
+    if (int rc = spl_inject(b + o_state, (const uint8_t *)(b + o_decks), (const uint8_t *)(b + o_nobles), N, P, stream)) return rc;
+    if (int rc = spl_playout_from(b + o_state, (const uint8_t *)(b + o_decks), seed, first_game, N, P, flags, max_steps,
+                                  (int8_t *)(b + o_score), (int16_t *)(b + o_steps), (uint8_t *)(b + o_kind),
+                                  (int64_t *)(b + o_ctr), nullptr, 0, stream))
+        return rc;
+    if (score2) CK(cudaMemcpyAsync(score2, b + o_score, (size_t)N * P, cudaMemcpyDeviceToHost, stream));
+    if (steps) CK(cudaMemcpyAsync(steps, b + o_steps, (size_t)N * 2, cudaMemcpyDeviceToHost, stream));
+    if (end_kind) CK(cudaMemcpyAsync(end_kind, b + o_kind, (size_t)N, cudaMemcpyDeviceToHost, stream));
+    int64_t ctr[16];
+    CK(cudaMemcpyAsync(ctr, b + o_ctr, 128, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (counters)
+        for (int i = 0; i < 16; i++) counters[i] += ctr[i];
+    return SPL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+"""BatchedSplendor: N Splendor games resident in HBM, driven through the C ABI (include/splendor_b200.h).
+
+torch is used for device memory and streams only; every rule computation happens in the CUDA kernels of
+csrc/kernels.cu.  Method names follow the reference's rule object (SplendorGameRule, splendor_model.py:142-576) where a
+batched equivalent exists: legal_mask ~ getLegalActions, step ~ update/generateSuccessor, game_ends, cal_score.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .state import state_shape
+
+NUM_ACTIONS = 3510
+MASK_WORDS = 110
+OBS_SIZE = 265
+DEFAULT_SEED = 1234  # the reference's SEED (agents/our_agents/ppo/constants.py:12)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class BatchedSplendor:
+    """N independent games of `num_agents` players.
+
+    Decks: by default counter-based (Philox keyed by (seed, first_game + env index)); `inject` switches the batch to
+    caller-supplied deck orders (the parity contract: same deck orders + same actions => same trajectory as the
+    reference engine).
+    """
+
+    def __init__(self, num_envs: int, num_agents: int = 2, seed: int = DEFAULT_SEED, first_game: int = 0,
+                 limit_rounds: bool = False, device: str | torch.device = "cuda"):
+        if not torch.cuda.is_available():
+            raise nat.SplendorNativeError("no CUDA device: the B200 engine has no CPU fallback")
+        self.lib = nat.lib()
+        self.N, self.P = int(num_envs), int(num_agents)
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.seed, self.first_game = int(seed), int(first_game)
+        self.flags = nat.F_LIMIT_ROUNDS if limit_rounds else 0
+        self.state = torch.zeros(state_shape(self.N, self.P), dtype=torch.int32, device=self.device)
+        self.decks = None  # explicit deck lists [N, 90] uint8 after inject()
+        self.reset()
+
+    # -- construction -------------------------------------------------------------------------------------------
+    def reset(self, first_game: int | None = None, want_lists: bool = False):
+        """SplendorGameRule(P).initialGameState() for every env (counter-based decks)."""
+        if first_game is not None:
+            self.first_game = int(first_game)
+        self.decks = None
+        lists = torch.empty((self.N, 90), dtype=torch.uint8, device=self.device) if want_lists else None
+        nobles = torch.empty((self.N, 5), dtype=torch.uint8, device=self.device) if want_lists else None
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_reset(_ptr(self.state), self.seed, self.first_game, self.N, self.P, _ptr(lists),
+                                         _ptr(nobles), _stream(self.device)), "spl_reset")
+        return (lists, nobles) if want_lists else None
+
+    def inject(self, deck_lists, nobles):
+        """Initial states from explicit deck orders ([N,90] card ids, reference list order) and noble ids ([N,>=P+1])."""
+        d = torch.as_tensor(np.ascontiguousarray(deck_lists, dtype=np.uint8)).to(self.device)
+        n = np.full((self.N, 5), 0xFF, np.uint8)
+        nb = np.asarray(nobles, dtype=np.uint8)
+        n[:, :nb.shape[1]] = nb
+        n = torch.as_tensor(n).to(self.device)
+        assert d.shape == (self.N, 90)
+        self.decks = d
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_inject(_ptr(self.state), _ptr(d), _ptr(n), self.N, self.P, _stream(self.device)), "spl_inject")
+
+    # -- the rule path ------------------------------------------------------------------------------------------
+    def legal_mask(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Bit-packed legal-action mask [N, 110] int32 (bit i%32 of word i/32 = ALL_ACTIONS[i] legal for the seat to move)."""
+        mask = out if out is not None else torch.empty((self.N, MASK_WORDS), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_legal_mask(_ptr(self.state), _ptr(mask), self.N, self.P, _stream(self.device)), "spl_legal_mask")
+        return mask
+
+    def step(self, actions: torch.Tensor):
+        """GameRule.update for one ALL_ACTIONS index per env (int16; <0 = skip).  Returns (reward i8, done u8, illegal u8)."""
+        a = actions.to(device=self.device, dtype=torch.int16).contiguous()
+        reward = torch.empty(self.N, dtype=torch.int8, device=self.device)
+        done = torch.empty(self.N, dtype=torch.uint8, device=self.device)
+        illegal = torch.empty(self.N, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_step(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, _ptr(a), _ptr(reward),
+                                        _ptr(done), _ptr(illegal), self.N, self.P, self.flags, _stream(self.device)), "spl_step")
+        return reward, done, illegal
+
+    def observe(self, seat: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+        """extract_metrics_with_cards(...).astype(float32) -> [N, 265]; seat: int8 per env (None = seat to move)."""
+        obs = out if out is not None else torch.empty((self.N, OBS_SIZE), dtype=torch.float32, device=self.device)
+        s = None if seat is None else seat.to(device=self.device, dtype=torch.int8).contiguous()
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_observe(_ptr(self.state), _ptr(s), _ptr(obs), self.N, self.P, _stream(self.device)), "spl_observe")
+        return obs
+
+    def final_scores(self):
+        """(2*calScore [N,P] int8, win2/tie1/loss0 [N,P] uint8, gameEnds kind [N] uint8)."""
+        score2 = torch.empty((self.N, self.P), dtype=torch.int8, device=self.device)
+        outcome = torch.empty((self.N, self.P), dtype=torch.uint8, device=self.device)
+        kind = torch.empty(self.N, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_final_scores(_ptr(self.state), _ptr(score2), _ptr(outcome), _ptr(kind), self.N, self.P,
+                                                self.flags, _stream(self.device)), "spl_final_scores")
+        return score2, outcome, kind
+
+    def playout(self, max_steps: int = 1000, trace_len: int = 0, counters: torch.Tensor | None = None):
+        """Random playouts to the end from the CURRENT states (RandomAgent on every seat).  Returns a dict of tensors."""
+        out = dict(
+            score2=torch.empty((self.N, self.P), dtype=torch.int8, device=self.device),
+            steps=torch.empty(self.N, dtype=torch.int16, device=self.device),
+            end_kind=torch.empty(self.N, dtype=torch.uint8, device=self.device),
+            counters=counters if counters is not None else torch.zeros(16, dtype=torch.int64, device=self.device),
+            trace=torch.empty((trace_len, self.N), dtype=torch.int16, device=self.device) if trace_len else None,
+        )
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_playout_from(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, self.N, self.P,
+                                                self.flags, max_steps, _ptr(out["score2"]), _ptr(out["steps"]),
+                                                _ptr(out["end_kind"]), _ptr(out["counters"]), _ptr(out["trace"]), trace_len,
+                                                _stream(self.device)), "spl_playout_from")
+        return out
+
+    def env_step(self, learner: torch.Tensor, actions: torch.Tensor, want_mask: bool = True, want_obs: bool = True):
+        """SplendorEnv.step for every env: learner move, random opponents, next mask + observation (see spl_env_step)."""
+        l = learner.to(device=self.device, dtype=torch.int8).contiguous()
+        a = actions.to(device=self.device, dtype=torch.int16).contiguous()
+        reward = torch.empty(self.N, dtype=torch.int8, device=self.device)
+        term = torch.empty(self.N, dtype=torch.uint8, device=self.device)
+        illegal = torch.empty(self.N, dtype=torch.uint8, device=self.device)
+        mask = torch.empty((self.N, MASK_WORDS), dtype=torch.int32, device=self.device) if want_mask else None
+        obs = torch.empty((self.N, OBS_SIZE), dtype=torch.float32, device=self.device) if want_obs else None
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_env_step(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, _ptr(l), _ptr(a),
+                                            _ptr(reward), _ptr(term), _ptr(illegal), _ptr(mask), _ptr(obs), self.N, self.P,
+                                            self.flags, _stream(self.device)), "spl_env_step")
+        return obs, reward, term, illegal, mask
+
+    def state_numpy(self) -> np.ndarray:
+        return self.state.cpu().numpy().view(np.uint32)
+
+
+def playout_games(num_games: int, num_agents: int = 2, seed: int = DEFAULT_SEED, first_game: int = 0,
+                  limit_rounds: bool = False, max_steps: int = 1000, trace_len: int = 0, want_final_state: bool = False,
+                  counters: torch.Tensor | None = None, device: str | torch.device = "cuda", outputs: bool = True):
+    """Fused reset + random playout + scoring for games first_game .. first_game+num_games-1 (spl_playout): nothing but the
+    results ever touches HBM."""
+    if not torch.cuda.is_available():
+        raise nat.SplendorNativeError("no CUDA device: the B200 engine has no CPU fallback")
+    lib = nat.lib()
+    dev = torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    G, P = int(num_games), int(num_agents)
+    out = dict(
+        score2=torch.empty((G, P), dtype=torch.int8, device=dev) if outputs else None,
+        steps=torch.empty(G, dtype=torch.int16, device=dev) if outputs else None,
+        end_kind=torch.empty(G, dtype=torch.uint8, device=dev) if outputs else None,
+        counters=counters if counters is not None else torch.zeros(16, dtype=torch.int64, device=dev),
+        trace=torch.empty((trace_len, G), dtype=torch.int16, device=dev) if trace_len else None,
+        final_state=torch.empty(state_shape(G, P), dtype=torch.int32, device=dev) if want_final_state else None,
+    )
+    with torch.cuda.device(dev):
+        nat.check(lib.spl_playout(int(seed), int(first_game), G, P, nat.F_LIMIT_ROUNDS if limit_rounds else 0, max_steps,
+                                  _ptr(out["score2"]), _ptr(out["steps"]), _ptr(out["end_kind"]), _ptr(out["counters"]),
+                                  _ptr(out["trace"]), trace_len, _ptr(out["final_state"]), _stream(dev)), "spl_playout")
+    return out
+
+
+def counters_dict(counters) -> dict:
+    c = counters.cpu().numpy() if hasattr(counters, "cpu") else np.asarray(counters)
+    return {k: int(v) for k, v in zip(nat.CTR_NAMES, c)}

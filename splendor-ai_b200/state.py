@@ -1,0 +1,124 @@
+"""Packed HBM state layout (include/splendor_b200.h) <-> plain numpy field arrays.
+
+One env = W = 8 + 4*P little-endian u32 words = C = W/4 chunks of 16 bytes; a batch is stored chunk-major,
+``words[c, e, 0:4]`` = chunk c of env e (uint4[C][N] on the device).  The fields restate the reference's object graph
+(splendor_model.py:52-138): board gems, dealt grid, decks, noble list, and per agent gems / bought cards / reserved
+list / score / nobles / passed / turn count.
+
+Gem and card counts are six 5-bit fields per word in the reference's COLOURS order black, red, yellow, green, blue,
+white (splendor_utils.py:124-131); the unpacked arrays use colour ids black0 red1 green2 blue3 white4 yellow5.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+NONE = 0xFF
+FIELD_OF_COLOUR_ID = (0, 1, 3, 4, 5, 2)  # colour id -> 5-bit field
+TIER_BASE = (0, 40, 70)
+TIER_SIZE = (40, 30, 20)
+META_EXPLICIT = 1 << 24
+META_ILLEGAL = 1 << 26
+
+
+def state_words(P: int) -> int:
+    if P not in (2, 3, 4):
+        raise ValueError("number of agents must be 2, 3 or 4")
+    return 8 + 4 * P
+
+
+def state_shape(N: int, P: int):
+    """Shape of the uint32 array/tensor holding N packed envs."""
+    return (state_words(P) // 4, N, 4)
+
+
+def _g6(word: np.ndarray) -> np.ndarray:
+    """[..., 6] counts by colour id from a g6 word."""
+    return np.stack([(word >> (5 * f)) & 31 for f in FIELD_OF_COLOUR_ID], axis=-1).astype(np.uint8)
+
+
+def _bytes4(word: np.ndarray) -> np.ndarray:
+    return np.stack([(word >> (8 * i)) & 0xFF for i in range(4)], axis=-1).astype(np.uint8)
+
+
+def _popcount(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint64)
+    c = np.zeros(x.shape, np.uint8)
+    for i in range(40):
+        c += ((x >> np.uint64(i)) & np.uint64(1)).astype(np.uint8)
+    return c
+
+
+def unpack(words: np.ndarray, P: int) -> dict:
+    """Decode packed states (uint32 [C, N, 4]) into field arrays (all leading dimension N)."""
+    words = np.asarray(words, dtype=np.uint32)
+    C, N, _ = words.shape
+    assert C == state_words(P) // 4
+    b0, b1 = words[0], words[1]
+    meta = b1[:, 3]
+    explicit = (meta & META_EXPLICIT) != 0
+    t1_mask = b1[:, 0].astype(np.uint64) | (((b1[:, 2] >> 20) & 0xFF).astype(np.uint64) << np.uint64(32))
+    t2_mask = (b1[:, 1] & 0x3FFFFFFF).astype(np.uint64)
+    t3_mask = (b1[:, 2] & 0xFFFFF).astype(np.uint64)
+    lazy_n = np.stack([_popcount(t1_mask), _popcount(t2_mask), _popcount(t3_mask)], axis=-1)
+    expl_n = _bytes4(b1[:, 0])[:, :3]
+    nobles = np.stack([(meta >> (4 * k)) & 15 for k in range(5)], axis=-1).astype(np.uint8)
+    nobles[nobles == 15] = NONE
+    out = dict(
+        P=P,
+        bank=_g6(b0[:, 0]),
+        dealt=np.concatenate([_bytes4(b0[:, 1]), _bytes4(b0[:, 2]), _bytes4(b0[:, 3])], axis=-1),
+        nobles=nobles,
+        n_nobles=(nobles != NONE).sum(-1).astype(np.uint8),
+        deck_n=np.where(explicit[:, None], expl_n, lazy_n).astype(np.uint8),
+        deck_masks=np.stack([t1_mask, t2_mask, t3_mask], axis=-1),
+        explicit=explicit,
+        illegal_flag=(meta & META_ILLEGAL) != 0,
+        cur=((meta >> 20) & 3).astype(np.uint8),
+        gems=np.zeros((N, P, 6), np.uint8), cards=np.zeros((N, P, 5), np.uint8), resv=np.zeros((N, P, 3), np.uint8),
+        n_resv=np.zeros((N, P), np.uint8), score=np.zeros((N, P), np.uint8), passed=np.zeros((N, P), np.uint8),
+        turns=np.zeros((N, P), np.uint16), nobles_mask=np.zeros((N, P), np.uint16), n_nobles_won=np.zeros((N, P), np.uint8),
+    )
+    for p in range(P):
+        w = words[2 + p]
+        out["gems"][:, p] = _g6(w[:, 0])
+        out["cards"][:, p] = _g6(w[:, 1])[:, :5]
+        rb = _bytes4(w[:, 2])
+        out["resv"][:, p] = rb[:, :3]
+        out["n_resv"][:, p] = (rb[:, :3] != NONE).sum(-1)
+        out["score"][:, p] = rb[:, 3]
+        out["turns"][:, p] = w[:, 3] & 0xFFFF
+        out["nobles_mask"][:, p] = (w[:, 3] >> 16) & 0x3FF
+        out["n_nobles_won"][:, p] = _popcount((w[:, 3] >> 16) & 0x3FF)
+        out["passed"][:, p] = (w[:, 3] >> 26) & 1
+    return out
+
+
+def snapshots(words: np.ndarray, P: int) -> np.ndarray:
+    """The canonical 108-byte field vector per env used by the golden files and parity tests ([N, 108] uint8):
+    bank6 | dealt12 | nobles5 | n_nobles | deck_n3 | cur | 4 x (gems6 cards5 resv3 n_resv score passed n_nobles turns_lo turns_hi)."""
+    u = unpack(words, P)
+    N = u["bank"].shape[0]
+    out = np.zeros((N, 108), np.uint8)
+    out[:, 0:6] = u["bank"]
+    out[:, 6:18] = u["dealt"]
+    out[:, 18:23] = u["nobles"]
+    out[:, 23] = u["n_nobles"]
+    out[:, 24:27] = u["deck_n"]
+    out[:, 27] = u["cur"]
+    for p in range(P):
+        o = 28 + 20 * p
+        out[:, o:o + 6] = u["gems"][:, p]
+        out[:, o + 6:o + 11] = u["cards"][:, p]
+        out[:, o + 11:o + 14] = u["resv"][:, p]
+        out[:, o + 14] = u["n_resv"][:, p]
+        out[:, o + 15] = u["score"][:, p]
+        out[:, o + 16] = u["passed"][:, p]
+        out[:, o + 17] = u["n_nobles_won"][:, p]
+        out[:, o + 18] = u["turns"][:, p] & 0xFF
+        out[:, o + 19] = u["turns"][:, p] >> 8
+    return out
+
+
+def remaining_deck_sets(deck_masks_row) -> list:
+    """Counter-based decks: per tier, the sorted card ids still in the deck (from one env's deck_masks)."""
+    return [[TIER_BASE[t] + i for i in range(TIER_SIZE[t]) if (int(deck_masks_row[t]) >> i) & 1] for t in range(3)]

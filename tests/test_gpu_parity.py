@@ -1,0 +1,257 @@
+"""`-m gpu` parity tests: the CUDA kernels, called through the C ABI, against the CPU oracle and the reference
+recordings.  Integer / index work: bit-exact.  The observation's two non-integer features (np.var, log1p) are compared
+by float32 bit pattern as well (tolerance 0)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_replays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import splendor_ai_b200 as p
+
+    p.build()
+    return p
+
+
+def unpack_mask(mask_row):
+    bits = np.unpackbits(np.ascontiguousarray(mask_row).view(np.uint8), bitorder="little")
+    return np.nonzero(bits)[0].astype(np.uint16)
+
+
+def snaps(eng, pkg):
+    return pkg.state.snapshots(eng.state_numpy(), eng.P)
+
+
+@pytest.mark.parametrize("P", [2, 3, 4])
+def test_reset_matches_oracle(pkg, oracle, P):
+    N = 300
+    eng = pkg.BatchedSplendor(N, P, seed=77, first_game=5)
+    lists, nobles = eng.reset(want_lists=True)
+    lists, nobles, sn = lists.cpu().numpy(), nobles.cpu().numpy(), snaps(eng, pkg)
+    u = pkg.state.unpack(eng.state_numpy(), P)
+    for e in range(N):
+        lo, no = oracle.synth_game(77, 5 + e, P)
+        assert np.array_equal(lists[e], lo) and np.array_equal(nobles[e][:P + 1], no), e
+        s = oracle.init(P, lo, no)
+        assert np.array_equal(sn[e], s.snapshot()), e
+        assert pkg.state.remaining_deck_sets(u["deck_masks"][e]) == s.remaining_deck_sets(), e
+
+
+@pytest.mark.parametrize("name", ["replays_2p", "replays_3p", "replays_4p"])
+def test_reference_recordings_replayed_on_gpu(pkg, name):
+    """The REFERENCE's own recorded games (deck orders injected, recorded actions replayed): every legal mask,
+    observation, reward, terminal flag, state and final score identical to what the Python engine produced."""
+    games = load_replays(name)
+    P = games[0]["P"]
+    for limit in (False, True):
+        gs = [g for g in games if g["limit"] == limit]
+        if not gs:
+            continue
+        N, T = len(gs), max(len(g["action"]) for g in gs)
+        eng = pkg.BatchedSplendor(N, P, limit_rounds=limit)
+        eng.inject(np.stack([g["decks"] for g in gs]), np.stack([np.concatenate([g["nobles"], [255] * (5 - len(g["nobles"]))]) for g in gs]))
+        assert np.array_equal(snaps(eng, pkg), np.stack([g["snap0"] for g in gs]))
+        for t in range(T):
+            live = [i for i, g in enumerate(gs) if t < len(g["action"])]
+            mask = eng.legal_mask().cpu().numpy()
+            seat = torch.tensor([int(g["seat"][t]) if t < len(g["action"]) else 0 for g in gs], dtype=torch.int8)
+            obs = eng.observe(seat).cpu().numpy()
+            for i in live:
+                assert np.array_equal(unpack_mask(mask[i]), gs[i]["legal"][t]), (name, i, t)
+                assert np.array_equal(obs[i].view(np.uint32), gs[i]["obs"][t].view(np.uint32)), (name, i, t)
+            act = torch.tensor([int(g["action"][t]) if t < len(g["action"]) else -1 for g in gs], dtype=torch.int16)
+            reward, done, illegal = (x.cpu().numpy() for x in eng.step(act))
+            sn = snaps(eng, pkg)
+            for i in live:
+                g = gs[i]
+                assert illegal[i] == 0 and reward[i] == g["reward"][t], (name, i, t)
+                assert (done[i] != 0) == bool(g["ends_limit"][t] if limit else g["ends_plain"][t]), (name, i, t)
+                assert np.array_equal(sn[i], g["snap"][t]), (name, i, t)
+        score2, _, _ = eng.final_scores()
+        score2 = score2.cpu().numpy()
+        for i, g in enumerate(gs):
+            assert list(score2[i]) == list(g["score2"]), (name, i)
+            fo = eng.observe(torch.full((N,), 0, dtype=torch.int8)).cpu().numpy()
+            assert np.array_equal(fo[i].view(np.uint32), g["final_obs"][0].view(np.uint32)), (name, i)
+
+
+@pytest.mark.parametrize("P,limit", [(2, False), (3, False), (4, False), (2, True)])
+def test_step_mask_observe_against_oracle_on_random_trajectories(pkg, oracle, P, limit):
+    """Batched mask -> choose -> step on counter-based decks vs the oracle stepping the same games (explicit lists)."""
+    N, seed, rng = 192, 4242, np.random.default_rng(P * 10 + limit)
+    eng = pkg.BatchedSplendor(N, P, seed=seed, first_game=1000, limit_rounds=limit)
+    orcs = [oracle.init(P, *oracle.synth_game(seed, 1000 + e, P)) for e in range(N)]
+    alive = np.ones(N, bool)
+    for t in range(400):
+        if not alive.any():
+            break
+        mask = eng.legal_mask().cpu().numpy()
+        obs = eng.observe().cpu().numpy()
+        act = np.full(N, -1, np.int16)
+        for e in np.nonzero(alive)[0]:
+            legal = oracle.legal(orcs[e])
+            assert np.array_equal(unpack_mask(mask[e]), legal), (e, t)
+            assert np.array_equal(obs[e].view(np.uint32), oracle.observe(orcs[e], orcs[e].cur).view(np.uint32)), (e, t)
+            act[e] = rng.choice(legal)
+        reward, done, illegal = (x.cpu().numpy() for x in eng.step(torch.from_numpy(act)))
+        sn = snaps(eng, pkg)
+        for e in np.nonzero(alive)[0]:
+            assert illegal[e] == 0 and reward[e] == oracle.step(orcs[e], int(act[e])), (e, t)
+            assert done[e] == oracle.game_ends(orcs[e], limit), (e, t)
+            assert np.array_equal(sn[e], orcs[e].snapshot()), (e, t)
+            if done[e]:
+                alive[e] = False
+    assert not alive.any()
+    score2, outcome, kind = (x.cpu().numpy() for x in eng.final_scores())
+    for e in range(N):
+        assert list(score2[e]) == [oracle.cal_score2(orcs[e], i) for i in range(P)]
+
+
+@pytest.mark.parametrize("P,limit,G", [(2, False, 4096), (3, False, 1024), (4, False, 2048), (2, True, 1024), (4, True, 512)])
+def test_fused_playout_traces_match_oracle(pkg, oracle, P, limit, G):
+    """Config 2 of BASELINE.json: whole random playouts on the GPU; every game's action trace, length, ending, final
+    state and calScore identical to the oracle's playout of the same (seed, game)."""
+    seed, first = 1234, 10_000
+    out = pkg.playout_games(G, P, seed=seed, first_game=first, limit_rounds=limit, max_steps=1000, trace_len=420, want_final_state=True)
+    trace = out["trace"].cpu().numpy()
+    steps, kind, score2 = out["steps"].cpu().numpy(), out["end_kind"].cpu().numpy(), out["score2"].cpu().numpy()
+    sn = pkg.state.snapshots(out["final_state"].cpu().numpy().view(np.uint32), P)
+    for g in range(G):
+        st, fin, tr, k = oracle.playout(seed, first + g, P, limit, 1000)
+        assert (steps[g], kind[g]) == (st, k), g
+        assert np.array_equal(trace[:st, g], tr[:st]) and (trace[st:, g] == -1).all(), g
+        assert list(score2[g]) == [oracle.cal_score2(fin, i) for i in range(P)], g
+        assert np.array_equal(sn[g], fin.snapshot()), g
+    _, _, ctr = oracle.playout_many(seed, first, G, P, limit, 1000, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(out["counters"].cpu().numpy(), ctr)
+
+
+def test_playout_full_size_counters_match_oracle(pkg, oracle):
+    """BASELINE config 2 at full size (65,536 two-player games): all 16 aggregate counters (wins/ties per seat, endings,
+    total steps, score sum, nobles) equal the oracle's over the same games; per-game lengths and scores equal too."""
+    G, seed = 65_536, 1234
+    out = pkg.playout_games(G, 2, seed=seed)
+    sc, st, ctr = oracle.playout_many(seed, 0, G, 2, False, 1000, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(out["counters"].cpu().numpy(), ctr)
+    assert np.array_equal(out["steps"].cpu().numpy().astype(np.int32), st)
+    assert np.array_equal(out["score2"].cpu().numpy(), sc)
+
+
+def test_explicit_deck_playout_equals_counter_based(pkg):
+    """spl_inject + spl_playout_from on the materialised deck orders == the fused counter-based playout."""
+    G, P, seed = 3000, 2, 99
+    eng = pkg.BatchedSplendor(G, P, seed=seed, first_game=0)
+    lists, nobles = eng.reset(want_lists=True)
+    eng.inject(lists.cpu().numpy(), nobles.cpu().numpy())
+    a = eng.playout(max_steps=1000, trace_len=300)
+    b = pkg.playout_games(G, P, seed=seed, first_game=0, trace_len=300)
+    for key in ("score2", "steps", "end_kind", "counters", "trace"):
+        assert torch.equal(a[key], b[key]), key
+
+
+def test_properties_at_full_size_4p(pkg):
+    """Config 3 (4 players, 2^20 envs): size-independent invariants + determinism + sharding invariance."""
+    G, P = 1 << 20, 4
+    a = pkg.playout_games(G, P, seed=5)
+    c = pkg.counters_dict(a["counters"])
+    steps = a["steps"].to(torch.int64)
+    assert c["games"] == G and c["steps"] == int(steps.sum())
+    assert c["end_score"] + c["end_deadlock"] + c["end_roundcap"] + c["end_truncated"] == G
+    assert c["end_roundcap"] == 0 and c["end_truncated"] == 0
+    assert c["score2_sum"] == int(a["score2"].to(torch.int64).sum())
+    wins = sum(c[f"wins{i}"] for i in range(4))
+    assert wins <= G and wins + sum(c[f"ties{i}"] for i in range(4)) >= G
+    kind = a["end_kind"]
+    best = a["score2"].max(dim=1).values
+    assert bool(((best >= 30) | (kind != 1)).all())           # a score ending means someone reached 15 points
+    assert bool((steps[kind == 1] % P == 0).all())            # ... and only at the end of a round (seat 0 to move)
+    b = pkg.playout_games(G, P, seed=5)                        # determinism
+    assert torch.equal(a["score2"], b["score2"]) and torch.equal(a["steps"], b["steps"])
+    h0 = pkg.playout_games(G // 2, P, seed=5, first_game=0)    # sharding by game id gives identical per-game results
+    h1 = pkg.playout_games(G // 2, P, seed=5, first_game=G // 2)
+    assert torch.equal(torch.cat([h0["score2"], h1["score2"]]), a["score2"])
+    assert torch.equal(h0["counters"] + h1["counters"], a["counters"])
+
+
+def test_illegal_actions_are_flagged_and_ignored(pkg, oracle):
+    N, P = 256, 2
+    eng = pkg.BatchedSplendor(N, P, seed=3)
+    before = eng.state.clone()
+    mask = eng.legal_mask().cpu().numpy()
+    rng = np.random.default_rng(0)
+    act = rng.integers(0, 3510, N).astype(np.int16)
+    act[:4] = [3510, 32000, 0, 5]
+    legal = np.array([a < 3510 and a in set(unpack_mask(mask[e]).tolist()) for e, a in enumerate(act)])
+    reward, done, illegal = (x.cpu().numpy() for x in eng.step(torch.from_numpy(act)))
+    assert np.array_equal(illegal == 0, legal)
+    after = eng.state.clone()
+    after[1, :, 3] &= ~(1 << 26)
+    bad = torch.from_numpy(~legal).to(after.device)
+    assert torch.equal(after[:, bad], before[:, bad])
+    assert (reward[~legal] == 0).all()
+
+
+def test_env_step_matches_oracle_emulation_of_splendor_env(pkg, oracle):
+    """spl_env_step vs SplendorEnv.step semantics (splendor_env.py:127-231) emulated with the oracle: learner move,
+    Philox-random opponents until the learner's seat, then the learner's mask + observation, 100-round cap."""
+    N, P, seed = 160, 2, 31
+    rng = np.random.default_rng(1)
+    learner = rng.integers(0, P, N).astype(np.int8)
+    eng = pkg.BatchedSplendor(N, P, seed=seed, first_game=0, limit_rounds=True)
+    orcs = [oracle.init(P, *oracle.synth_game(seed, e, P)) for e in range(N)]
+
+    def simulate_opponents(e):
+        s = orcs[e]
+        while s.cur != learner[e] and not oracle.game_ends(s, True):
+            legal = oracle.legal(s)
+            t = sum(s.pl[i].turns for i in range(P))
+            r = int(oracle.philox(seed, e, t, 0)[0])
+            oracle.step(s, int(legal[(r * len(legal)) >> 32]))
+
+    act = np.full(N, -1, np.int16)  # reset step: opponents play up to the learner's first turn
+    alive = np.ones(N, bool)
+    for it in range(120):
+        obs, reward, term, illegal, mask = (x.cpu().numpy() for x in eng.env_step(torch.from_numpy(learner), torch.from_numpy(act)))
+        for e in np.nonzero(alive)[0]:
+            if act[e] >= 0:
+                assert reward[e] == oracle.step(orcs[e], int(act[e])), (e, it)
+            simulate_opponents(e)
+            assert illegal[e] == 0 and term[e] == oracle.game_ends(orcs[e], True), (e, it)
+            assert np.array_equal(unpack_mask(mask[e]), oracle.legal(orcs[e], int(learner[e]))), (e, it)
+            assert np.array_equal(obs[e].view(np.uint32), oracle.observe(orcs[e], int(learner[e])).view(np.uint32)), (e, it)
+            if term[e]:
+                alive[e] = False
+                act[e] = -1
+            else:
+                act[e] = rng.choice(oracle.legal(orcs[e]))
+        sn = snaps(eng, pkg)
+        for e in range(N):
+            assert np.array_equal(sn[e], orcs[e].snapshot()), (e, it)
+        if not alive.any():
+            break
+    assert not alive.any()
+
+
+def test_host_buffer_abi_call(pkg, oracle):
+    """spl_playout_host: host deck orders in, host results out (the end-to-end path bench.py times)."""
+    import ctypes as C
+
+    N, P, seed = 2048, 2, 8
+    lists = np.stack([oracle.synth_game(seed, g, P)[0] for g in range(N)])
+    nobles = np.full((N, 5), 255, np.uint8)
+    for g in range(N):
+        nobles[g, :P + 1] = oracle.synth_game(seed, g, P)[1]
+    score2, steps, kind = np.zeros((N, P), np.int8), np.zeros(N, np.int16), np.zeros(N, np.uint8)
+    ctr = np.zeros(16, np.int64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = pkg._native.lib().spl_playout_host(p(lists), p(nobles), seed, 0, N, P, 0, 1000, p(score2), p(steps), p(kind), p(ctr), None)
+    assert rc == 0, pkg._native.lib().spl_error_string(rc)
+    sc, st, c = oracle.playout_many(seed, 0, N, P, False, 1000, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(score2, sc) and np.array_equal(steps.astype(np.int32), st) and np.array_equal(ctr, c)
