@@ -38,7 +38,8 @@ enum ActType { T_PASS = 0, T_RESERVE = 1, T_SAME = 2, T_DIFF = 3, T_BUY_RESERVE 
 constexpr int BASE_RESERVE = 6, BASE_SAME = 510, BASE_DIFF = 1140, BASE_BUY_RESERVE = 3420, BASE_BUY_AVAILABLE = 3438;
 
 struct Tables {
-    uint2 card[96];          // .x = cost (g6, yellow field 0) ; .y = 5*colour_field | points << 5 | tier << 8
+    uint2 card[128];         // .x = cost (g6, yellow field 0) ; .y = 5*colour_field | points << 5 | tier << 8;
+                             // entries 90..127 (an empty slot's 0xFF & 127 lands on 127): colour shift = yellow, never buyable
     uint32_t noble[16];      // requirement (g6); entry 15 = "no noble" (unsatisfiable)
     uint32_t combo_c[25];    // collect_diff combo ci: collected gems (g6).  ci 0..4 L=1, 5..14 L=2, 15..24 L=3
     uint16_t combo_base[25]; // ALL_ACTIONS index of (combo ci, noble slot 0, variant 0)
@@ -74,7 +75,7 @@ __host__ __device__ constexpr uint32_t g6_from_normal(const int *c)
 __host__ __device__ constexpr Tables make_tables()
 {
     Tables T{};
-    for (int i = 0; i < 96; i++) T.card[i] = uint2{0x1EF7BDEFu & ~(31u << YSH), 0};  // filler: costs 15 of everything
+    for (int i = 0; i < 128; i++) T.card[i] = uint2{0u, (uint32_t)YSH};  // filler: a free card of "colour yellow", which count_legal treats as capped
     for (int i = 0; i < SPL_NUM_CARDS; i++) {
         const detail::CardRow &r = detail::CARD_ROWS[i];
         int tier = i < 40 ? 0 : (i < 70 ? 1 : 2);
@@ -149,6 +150,15 @@ __device__ __forceinline__ uint32_t hsum6(uint32_t x)  // sum of the six fields 
     x = (x & 0x7FFFu) + (x >> 15);
     return (x & 31u) + ((x >> 5) & 31u) + (x >> 10);
 }
+__device__ __forceinline__ uint32_t hsum6_small(uint32_t x)  // same, valid when the total is <= 31
+{
+    return ((x * ONES6) >> 25) & 31u;
+}
+__device__ __forceinline__ uint32_t nibble_sum(uint32_t x)  // sum of the eight 4-bit fields (total <= 255)
+{
+    x = (x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu);
+    return (x * 0x01010101u) >> 24;
+}
 __device__ __forceinline__ uint32_t compress6(uint32_t h)  // guard bits (subset of H6) -> 6-bit field mask
 {
     return ((((h >> 4) & 0x00108421u) * 0x00111110u) >> 20 & 31u) | ((h >> 24) & 32u);
@@ -190,8 +200,13 @@ __device__ __forceinline__ uint32_t occupied4(uint32_t dealt_word)  // 4-bit mas
     return ((((~dealt_word) & 0x80808080u) >> 7) * 0x00204081u) >> 21 & 15u;
 }
 
+// Out of line by default: ~70 instructions called from the action draw, every deal and the reset; inlining all call
+// sites made the playout kernel overflow the instruction cache (profiles/r1a).
+#ifndef SPL_PHILOX_INLINE
+#define SPL_PHILOX_INLINE __noinline__
+#endif
 // Philox4x32-10 (Salmon et al. 2011).  counter = (game lo, game hi, index, stream), key = seed.
-__device__ __forceinline__ uint4 philox(uint64_t seed, uint64_t game, uint32_t index, uint32_t stream)
+__device__ SPL_PHILOX_INLINE uint4 philox(uint64_t seed, uint64_t game, uint32_t index, uint32_t stream)
 {
     uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = index, c3 = stream;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -300,12 +315,12 @@ __device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t gam
     }
     e.meta = list | ((uint32_t)(P - 2) << 22);
     DeckSrc src{nullptr, seed, game};
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) w |= deal(e, t, src) << (8 * c);
-        e.d[t] = w;
+    e.d[0] = e.d[1] = e.d[2] = 0;
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) {  // one copy of deal() in the binary: the reset runs once per game, the step loop 90 times
+        const int t = i >> 2;
+        const uint32_t card = deal(e, t, src) << (8 * (i & 3));
+        if (t == 0) e.d[0] |= card; else if (t == 1) e.d[1] |= card; else e.d[2] |= card;
     }
 #pragma unroll
     for (int p = 0; p < P; p++) { e.pg[p] = 0; e.pc[p] = 0; e.pr[p] = 0x00FFFFFFu; e.pi[p] = 0; }
@@ -362,15 +377,34 @@ __device__ __forceinline__ void make_ctx(const Env<P> &e, const Tables &T, Ctx &
     c.Lmin = c.hold <= 7 ? c.Lmax : (c.hold == 8 ? min(c.nA, 2) : min(c.nA, 1));
 }
 
-// number of distinct multisets of e gems drawn from what the agent holds in the colours of field mask O (:329-367)
+// Family totals, per-length collect_diff totals and per-slot buy counts of one decision.
+struct FamilyCounts {
+    int res, same, diff, bres, bav;  // actions per family (noble multiplicity included)
+    int dL[3];                       // collect_diff actions taking 1 / 2 / 3 gems
+    uint32_t buy_lo, buy_hi;         // buy actions per card, 4 bits each: board slots 0..7 | slots 8..11 + reserved 0..2
+};
+
+// binomial(n, L) for n <= 5 (negative n -> 0), L a compile-time 1..3
+template <int L>
+__device__ __forceinline__ int binom(int n)
+{
+    n = max(n, 0);
+    if (L == 1) return n;
+    return (int)(((L == 2 ? 0xA63100u : 0xA41000u) >> (4 * n)) & 15u);
+}
+__device__ __forceinline__ int choose2(int x) { return (x * (x - 1)) >> 1; }
+__device__ __forceinline__ int choose3(int x) { return (x * (x - 1) * (x - 2) * 10923) >> 16; }  // exact for x <= 40
+
+// Number of distinct multisets of e (0..3) gems the agent can return out of colours O, given how many of those colours
+// it holds >=1 / >=2 / >=3 of (generate_return_combos :329-367).  Branch-free.
+__device__ __forceinline__ int n_returns(int e, int a1, int a2, int a3)
+{
+    const int r2 = choose2(a1) + a2, r3 = choose3(a1) + a2 * (a1 - 1) + a3;
+    return e <= 0 ? 1 : (e == 1 ? a1 : (e == 2 ? r2 : r3));
+}
 __device__ __forceinline__ int n_returns(int e, const Ctx &c, uint32_t O)
 {
-    if (e <= 0) return 1;
-    const int a1 = __popc(c.h1 & O);
-    if (e == 1) return a1;
-    const int a2 = __popc(c.h2 & O);
-    if (e == 2) return (a1 * (a1 - 1) >> 1) + a2;
-    return (a1 * (a1 - 1) * (a1 - 2)) / 6 + a2 * (a1 - 1) + __popc(c.h3 & O);
+    return n_returns(e, __popc(c.h1 & O), __popc(c.h2 & O), __popc(c.h3 & O));
 }
 // the vi-th feasible variant in [v0, v1) of a returned-gems table row
 __device__ __forceinline__ int nth_feasible(const uint32_t *row, int v0, int v1, int vi, uint32_t gems)
@@ -396,43 +430,71 @@ __device__ __forceinline__ bool can_buy(const Ctx &c, uint2 cw, uint32_t &pay)
     return field(c.cards, cw.y & 31u) != 7u && wild <= (uint32_t)c.yellow;
 }
 
-struct FamilyCounts { int res, same, diff, bres, bav; };
+// collect_diff actions that take exactly L gems (before the noble multiplicity), in closed form.
+// Instead of looping over the colour combinations C and counting the return multisets R each one allows, sum over the
+// (few) classes of R: a multiset whose support meets the available colours A in j colours is compatible with
+// binomial(nA - j, L) combinations.  M[j] = number of feasible R of size e with |supp(R) & A| = j, from
+//   q_i = colours of A held >= i times,  r_i = other colours (yellow, or bank empty) held >= i times.
+template <int L>
+__device__ __forceinline__ int diff_count(const Ctx &c, int q1, int q2, int q3, int r1, int r2, int r3)
+{
+    const int e = c.hold + L - 10;  // gems to return; <= L
+    int m0 = 1, m1 = 0, m2 = 0, m3 = 0;
+    if (L >= 1) { const bool s = e == 1; m0 = s ? r1 : m0; m1 = s ? q1 : m1; }
+    if (L >= 2) {
+        const bool s = e == 2;
+        m0 = s ? r2 + choose2(r1) : m0; m1 = s ? q2 + q1 * r1 : m1; m2 = s ? choose2(q1) : m2;
+    }
+    if (L >= 3) {
+        const bool s = e == 3;
+        m0 = s ? r3 + r2 * (r1 - 1) + choose3(r1) : m0;
+        m1 = s ? q3 + q2 * r1 + r2 * q1 + q1 * choose2(r1) : m1;
+        m2 = s ? q2 * (q1 - 1) + choose2(q1) * r1 : m2;
+        m3 = s ? choose3(q1) : m3;
+    }
+    const int n = m0 * binom<L>(c.nA) + m1 * binom<L>(c.nA - 1) + m2 * binom<L>(c.nA - 2) + m3 * binom<L>(c.nA - 3);
+    return (L >= c.Lmin && L <= c.Lmax) ? n : 0;
+}
 
 template <int P>
 __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, const Ctx &c, FamilyCounts &f)
 {
     f.res = c.n_resv < 3 ? __popc(c.occ) * c.nS * reserve_variants(c) : 0;
-    f.same = 0;
+    const int t1 = __popc(c.h1), t2 = __popc(c.h2), t3 = __popc(c.h3);
+    // collect_same (:475-496): colour fl excluded from the returnable colours
+    int same = 0;
 #pragma unroll
     for (int n = 0; n < 5; n++) {
         const int fl = field_of_normal(n);
-        if (c.A4 >> fl & 1) f.same += n_returns(c.hold - 8, c, 63u & ~(1u << fl));
+        const int nv = n_returns(c.hold - 8, t1 - (int)(c.h1 >> fl & 1u), t2 - (int)(c.h2 >> fl & 1u), t3 - (int)(c.h3 >> fl & 1u));
+        same += (c.A4 >> fl & 1u) ? nv : 0;
     }
-    f.same *= c.nS;
-    f.diff = 0;
-    if (c.hold <= 7) {
-        f.diff = (int)((0xA41110u >> (4 * c.nA)) & 15u);  // C(nA, min(nA,3)), 0 when the bank is empty
-    } else {
-        for (int ci = 0; ci < 25; ci++) {
-            const uint32_t m = T.combo_mask[ci];
-            const int L = combo_len(ci);
-            if ((m & ~c.A1) || L < c.Lmin) continue;
-            f.diff += n_returns(c.hold + L - 10, c, 63u & ~m);
-        }
+    f.same = same * c.nS;
+    // collect_diff (:437-473)
+    {
+        const int q1 = __popc(c.h1 & c.A1), q2 = __popc(c.h2 & c.A1), q3 = __popc(c.h3 & c.A1);
+        f.dL[0] = diff_count<1>(c, q1, q2, q3, t1 - q1, t2 - q2, t3 - q3) * c.nS;
+        f.dL[1] = diff_count<2>(c, q1, q2, q3, t1 - q1, t2 - q2, t3 - q3) * c.nS;
+        f.dL[2] = diff_count<3>(c, q1, q2, q3, t1 - q1, t2 - q2, t3 - q3) * c.nS;
+        f.diff = f.dL[0] + f.dL[1] + f.dL[2];
     }
-    f.diff *= c.nS;
-    f.bres = 0; f.bav = 0;
+    // buy (:522-568): 12 board slots + 3 reserved cards, branch-free; empty slots (0xFF) index an unaffordable filler
+    const uint32_t eff = (c.gems & ~(31u << YSH)) + c.cards;    // gems + bought cards per colour (<= 14)
+    const uint32_t cap = ((c.cards + 9u * ONES6) & H6) | (16u << YSH);  // guard bit set where 7 cards of the colour are owned (+ filler)
+    uint32_t lo = 0, hi = 0;
 #pragma unroll
     for (int s = 0; s < 15; s++) {
-        const uint32_t id = s < 12 ? byte_of(e.d[s >> 2], s & 3) : byte_of(c.resv, s - 12);
-        if (id == NONE8) continue;
-        const uint2 cw = T.card[id];
-        uint32_t pay;
-        if (!can_buy(c, cw, pay)) continue;
-        const uint32_t Sb = c.S | ((c.near >> (cw.y & 31u)) & 31u);
-        const int k = Sb ? __popc(Sb) : 1;
-        if (s < 12) f.bav += k; else f.bres += k;
+        const uint32_t w = s < 12 ? e.d[s >> 2] : c.resv;
+        const uint2 cw = T.card[(w >> (8 * (s & 3))) & 127u];
+        const uint32_t sh = cw.y & 31u;
+        const uint32_t wild = hsum6_small(satsub6(cw.x, eff));   // max(cost - cards - gems, 0) summed = wilds needed
+        const bool ok = wild <= (uint32_t)c.yellow && !((cap >> sh) & 16u);
+        const uint32_t cnt = ok ? (uint32_t)max(__popc(c.S | ((c.near >> sh) & 31u)), 1) : 0u;
+        if (s < 8) lo |= cnt << (4 * s); else hi |= cnt << (4 * (s - 8));
     }
+    f.buy_lo = lo; f.buy_hi = hi;
+    f.bav = (int)(nibble_sum(lo) + nibble_sum(hi & 0xFFFFu));
+    f.bres = (int)nibble_sum(hi >> 16);
     return f.res + f.same + f.diff + f.bres + f.bav;
 }
 
@@ -467,95 +529,91 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
         return;
     }
     k -= f.res;
-    if (k < f.same) {  // collect_same: 510 + c*126 + n*21 + v
-        const int e2 = c.hold - 8;
-        int col = 0, nv = 1;
-        for (; col < 5; col++) {
-            const int fl = field_of_normal(col);
-            if (!(c.A4 >> fl & 1)) continue;
-            nv = n_returns(e2, c, 63u & ~(1u << fl));
-            if (k < nv * c.nS) break;
-            k -= nv * c.nS;
-        }
-        const int ni = small_div(k, nv), vi = k - ni * nv;
-        const uint32_t *row = T.ret_same + col * 21;
-        int v = 0;
-        if (e2 == 1) v = nth_feasible(row, 11, 16, vi, c.gems);
-        else if (e2 == 2) {
-            v = nth_feasible(row, 1, 11, vi, c.gems);
-            if (v == 11) {  // fewer than vi+1 feasible pairs: continue among "two of one colour"
-                const int a1 = __popc(c.h1 & 63u & ~(1u << field_of_normal(col)));
-                v = nth_feasible(row, 16, 21, vi - (a1 * (a1 - 1) >> 1), c.gems);
-            }
-        }
-        ch.type = T_SAME; ch.slot = col;
-        ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
-        ch.C = 2u << (5 * field_of_normal(col));
-        ch.R = row[v];
-        ch.idx = BASE_SAME + col * 126 + ch.n * 21 + v;
-        return;
-    }
-    k -= f.same;
-    if (k < f.diff) {  // collect_diff: combo_base + n*V + v
-        int ci, nv = 1, L;
-        if (c.hold <= 7) {
-            const int q = small_div(k, c.nS);
-            k -= q * c.nS;
-            int seen = 0;
-            L = c.Lmax;
-            ci = L == 1 ? 0 : (L == 2 ? 5 : 15);
-            for (; ci < 24; ci++) {
-                if (T.combo_mask[ci] & ~c.A1) continue;
-                if (seen++ == q) break;
-            }
-        } else {
-            for (ci = 0; ci < 25; ci++) {
-                const uint32_t m = T.combo_mask[ci];
-                L = combo_len(ci);
-                if ((m & ~c.A1) || L < c.Lmin) continue;
-                nv = n_returns(c.hold + L - 10, c, 63u & ~m);
+    if (k < f.same + f.diff) {
+        // collect_same (510 + c*126 + n*21 + v) and collect_diff (combo_base + n*V + v): find the group (colour or colour
+        // combination), then the noble slot and the vi-th feasible return variant within a range of its table row
+        const uint32_t *row;
+        int base, V, nv = 1, v0 = 0, v1 = 0, vsplit = -1;
+        if (k < f.same) {
+            const int e2 = c.hold - 8;
+            int col = 0;
+            for (; col < 4; col++) {
+                const int fl = field_of_normal(col);
+                if (!(c.A4 >> fl & 1)) continue;
+                nv = n_returns(e2, c, 63u & ~(1u << fl));
                 if (k < nv * c.nS) break;
                 k -= nv * c.nS;
             }
+            if (col == 4) nv = n_returns(e2, c, 63u & ~(1u << field_of_normal(4)));
+            row = T.ret_same + col * 21;
+            base = BASE_SAME + col * 126; V = 21;
+            if (e2 == 1) { v0 = 11; v1 = 16; }
+            if (e2 == 2) { v0 = 1; v1 = 11; vsplit = choose2(__popc(c.h1 & 63u & ~(1u << field_of_normal(col)))); }
+            ch.type = T_SAME; ch.slot = col;
+            ch.C = 2u << (5 * field_of_normal(col));
+        } else {
+            k -= f.same;
+            int L = 1;
+            if (k >= f.dL[0]) { k -= f.dL[0]; L = 2; if (k >= f.dL[1]) { k -= f.dL[1]; L = 3; } }
+            const int ex = c.hold + L - 10;
+            int ci = L == 1 ? 0 : (L == 2 ? 5 : 15);
+            const int ci_end = L == 1 ? 4 : (L == 2 ? 14 : 24);
+            for (; ci < ci_end; ci++) {  // the last candidate needs no test
+                const uint32_t m = T.combo_mask[ci];
+                if (m & ~c.A1) continue;
+                nv = ex <= 0 ? 1 : n_returns(ex, c, 63u & ~m);
+                if (k < nv * c.nS) break;
+                k -= nv * c.nS;
+            }
+            if (ci == ci_end && ex > 0) nv = n_returns(ex, c, 63u & ~(uint32_t)T.combo_mask[ci]);
+            const int kk = 6 - L, r1 = 1 + kk, r2 = r1 + (kk * (kk + 1) >> 1);
+            V = L == 1 ? 6 : (L == 2 ? 15 : 20);
+            row = T.ret_diff + T.combo_off[ci];
+            base = T.combo_base[ci];
+            if (ex == 1) { v0 = 1; v1 = r1; }
+            if (ex == 2) { v0 = r1; v1 = r2; }
+            if (ex == 3) { v0 = r2; v1 = V; }
+            ch.type = T_DIFF; ch.slot = ci;
+            ch.C = T.combo_c[ci];
         }
-        const int ni = small_div(k, nv), vi = k - ni * nv;
-        const int ex = c.hold + L - 10, kk = 6 - L, V = L == 1 ? 6 : (L == 2 ? 15 : 20);
-        const uint32_t *row = T.ret_diff + T.combo_off[ci];
-        int v = 0;
-        if (ex > 0) {
-            const int r1 = 1 + kk, r2 = r1 + (kk * (kk + 1) >> 1);  // first variant returning 2 / 3 gems
-            v = ex == 1 ? nth_feasible(row, 1, r1, vi, c.gems)
-                        : (ex == 2 ? nth_feasible(row, r1, r2, vi, c.gems) : nth_feasible(row, r2, V, vi, c.gems));
+        const int ni = small_div(k, nv);
+        int vi = k - ni * nv, v = 0;
+        if (v1 > v0) {
+            if (vsplit >= 0 && vi >= vsplit) { vi -= vsplit; v0 = 16; v1 = 21; }  // collect_same: past the pairs -> "two of one colour"
+            v = nth_feasible(row, v0, v1, vi, c.gems);
         }
-        ch.type = T_DIFF; ch.slot = ci;
         ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
-        ch.C = T.combo_c[ci];
         ch.R = row[v];
-        ch.idx = T.combo_base[ci] + ch.n * V + v;
+        ch.idx = base + ch.n * V + v;
         return;
     }
-    k -= f.diff;
-    // buys: reserved cards first (3420 + r*6 + n), then the board (3438 + p*6 + n)
-#pragma unroll 1
-    for (int i = 0; i < 15; i++) {
-        const int s = i < 3 ? 12 + i : i - 3;
-        uint32_t w = s < 4 ? e.d[0] : (s < 8 ? e.d[1] : (s < 12 ? e.d[2] : c.resv));
-        const uint32_t id = byte_of(w, s & 3);
-        if (id == NONE8) continue;
-        const uint2 cw = T.card[id];
-        uint32_t pay;
-        if (!can_buy(c, cw, pay)) continue;
+    k -= f.same + f.diff;
+    // buys: reserved cards first (3420 + r*6 + n), then the board (3438 + p*6 + n); per-card counts come packed from count_legal
+    int s = 12;
+    {
+        uint32_t w = f.buy_hi >> 16;
+        int i = 0;
+        for (; i < 15; i++) {
+            if (i == 3) w = f.buy_lo;
+            if (i == 11) w = f.buy_hi;
+            const int cnt = (int)(w & 15u);
+            if (k < cnt) break;
+            k -= cnt;
+            w >>= 4;
+        }
+        s = i < 3 ? 12 + i : i - 3;
+    }
+    {
+        const uint32_t w = s < 4 ? e.d[0] : (s < 8 ? e.d[1] : (s < 12 ? e.d[2] : c.resv));
+        const uint2 cw = T.card[byte_of(w, s & 3) & 127u];
         const uint32_t Sb = c.S | ((c.near >> (cw.y & 31u)) & 31u);
-        const int cnt = Sb ? __popc(Sb) : 1;
-        if (k >= cnt) { k -= cnt; continue; }
+        can_buy(c, cw, ch.R);
         ch.type = s < 12 ? T_BUY_AVAILABLE : T_BUY_RESERVE;
         ch.slot = s < 12 ? s : s - 12;
         ch.n = Sb ? select_bit8(Sb, k) + 1 : 0;
-        ch.R = pay; ch.info = cw.y;
+        ch.info = cw.y;
         ch.idx = (s < 12 ? BASE_BUY_AVAILABLE + s * 6 : BASE_BUY_RESERVE + (s - 12) * 6) + ch.n;
-        return;
     }
-    ch.type = T_PASS; ch.n = 0; ch.idx = 0;  // unreachable when counts are consistent
 }
 
 // Is ALL_ACTIONS[idx] legal for the seat to move?  Decodes it into ch either way (build_action, gym/envs/utils.py:43-145).
@@ -612,7 +670,7 @@ __device__ __forceinline__ bool decode_and_check(const Env<P> &e, const Tables &
         if ((s >> 2) == 2) w = e.d[2];
         const uint32_t id = avail ? byte_of(w, s & 3) : byte_of(c.resv, s);
         ok = id != NONE8;
-        const uint2 cw = T.card[ok ? id : 95];
+        const uint2 cw = T.card[id & 127u];
         ok = ok && can_buy(c, cw, ch.R);
         ch.info = cw.y;
         S |= (c.near >> (cw.y & 31u)) & 31u;

@@ -12,6 +12,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
