@@ -214,7 +214,7 @@ def run_b200(args):
         eng_lists = torch.empty((G, 90), dtype=torch.uint8, device=dev)
         eng_nobles = torch.empty((G, 5), dtype=torch.uint8, device=dev)
         st = torch.empty(pkg.state.state_shape(G, P), dtype=torch.int32, device=dev)
-        pkg._native.check(lib.spl_reset(st.data_ptr(), SEED, first_game(10_000 + s), G, P, eng_lists.data_ptr(), eng_nobles.data_ptr(), stream), "spl_reset")
+        pkg._native.check(lib.spl_reset(st.data_ptr(), SEED, first_game(10_000 + s), None, None, G, P, eng_lists.data_ptr(), eng_nobles.data_ptr(), stream), "spl_reset")
         host_in.append((eng_lists.cpu().pin_memory(), eng_nobles.cpu().pin_memory()))
     h_score = torch.empty((G, P), dtype=torch.int8).pin_memory()
     h_steps = torch.empty(G, dtype=torch.int16).pin_memory()

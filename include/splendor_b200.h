@@ -17,7 +17,8 @@
  * State layout in HBM ("packed SoA of 128-bit chunks")
  *   One env = W = 8 + 4*P little-endian u32 words = C = W/4 chunks of 16 bytes.  `state` is uint4[C][N]: chunk c of
  *   env e lives at ((c * N) + e) * 16 bytes, so a warp of consecutive envs reads/writes 512 contiguous bytes per chunk.
- *     word 0   bank            six 5-bit fields (bit 5*colour), values 0..7
+ *     word 0   bank            six 5-bit fields, field f at bits 5f..5f+4, in the reference's COLOURS order black, red,
+ *                              yellow, green, blue, white (splendor_utils.py:124-131); values 0..7
  *     word 1-3 dealt[tier]     four bytes, byte col = card id of face-up slot (tier, col), 0xFF = empty slot
  *     word 4-6 deck            counter-based decks: bitmask of cards still in each deck
  *                                word4 = tier-1 bits 0..31, word5 = tier-2 (30 bits),
@@ -26,7 +27,7 @@
  *     word 7   meta            bits 0..19 board nobles, LIST ORDER, one nibble each (0xF = none) | bits 20..21 seat to
  *                              move | bits 22..23 P-2 | bit 24 explicit-deck flag | bit 26 sticky illegal-action flag
  *     player p at words 8+4p .. 11+4p
- *       +0 gems    six 5-bit fields            +1 bought cards per colour, five 5-bit fields
+ *       +0 gems    six 5-bit fields (same order)  +1 bought cards per colour, same fields (the yellow field stays 0)
  *       +2 reserved card ids, bytes 0..2 in list order (0xFF = none), byte 3 = score
  *       +3 bits 0..15 turns taken | bits 16..25 nobles owned (bit = noble id) | bit 26 passed
  */
@@ -78,12 +79,14 @@ int spl_last_cuda_error(void);          /* cudaError_t of the last failing runti
 const char *spl_error_string(int code);
 
 /* SplendorGameRule(P).initialGameState() for N synthetic games (splendor_model.py:69-93), decks and nobles drawn from
- * Philox4x32-10 keyed (seed, game id = first_game + e) instead of Python's `random` (DESIGN.md "Synthetic games").
+ * Philox4x32-10 keyed (seed, game id) instead of Python's `random` (DESIGN.md "Synthetic games").  The game id of env e
+ * is game_ids[e] if game_ids is non-null, else first_game + e (the same convention holds for every call below that
+ * takes both).  where (nullable, N bytes): only envs with where[e] != 0 are reset - the vector env's auto-reset.
  * If deck_lists_out (N*90 bytes) / nobles_out (N*5 bytes) are non-null they receive the full deck orders in the
  * REFERENCE's list order (deal() pops from the end) and the noble ids, so the same games can be replayed through the
  * reference engine. */
-int spl_reset(void *state, uint64_t seed, uint64_t first_game, int64_t N, int P,
-              uint8_t *deck_lists_out, uint8_t *nobles_out, void *stream);
+int spl_reset(void *state, uint64_t seed, uint64_t first_game, const uint64_t *game_ids, const uint8_t *where,
+              int64_t N, int P, uint8_t *deck_lists_out, uint8_t *nobles_out, void *stream);
 
 /* Initial states from caller-supplied deck orders (reference list order, N*90 bytes) and noble ids (N*5 bytes,
  * first P+1 used): what BoardState.__init__ leaves after its 12 deals.  `deck_lists` must stay alive and be passed as
@@ -99,8 +102,9 @@ int spl_legal_mask(const void *state, uint32_t *mask, int64_t N, int P, void *st
  * move (gameEnds, SPL_END_*); illegal[e] = 1 and the env is left untouched if the index is out of range or not legal
  * (the ValueError of splendor_env.py:139-153).  action[e] < 0 skips the env.  Output pointers may be null.
  * decks: null for counter-based decks, else the array given to spl_inject.  seed/first_game: as given to spl_reset. */
-int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const int16_t *action,
-             int8_t *reward, uint8_t *done, uint8_t *illegal, int64_t N, int P, uint32_t flags, void *stream);
+int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
+             const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal, int64_t N, int P, uint32_t flags,
+             void *stream);
 
 /* gameEnds() per env (SPL_END_*), and calScore per seat as 2*score (+1 = the half-point tie-break), plus the
  * win(2)/tie(1)/loss(0) class of general_game_runner.py:416-430.  Output pointers may be null. */
@@ -122,8 +126,8 @@ int spl_playout(uint64_t seed, uint64_t first_game, int64_t num_games, int P, ui
                 int16_t *trace, int trace_len, void *final_state, void *stream);
 
 /* Same, continuing from existing states (e.g. after spl_inject, with `decks`); states are updated in place. */
-int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, int64_t N, int P,
-                     uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind,
+int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
+                     int64_t N, int P, uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind,
                      int64_t *counters, int16_t *trace, int trace_len, void *stream);
 
 /* The PPO rollout call: SplendorEnv.step(action) (splendor_env.py:127-172) for N envs at once -- the learner's move,
@@ -131,9 +135,9 @@ int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t 
  * (_simulate_opponents :219-231), then the learner's next legal mask and observation.  learner[e] = the learner's
  * seat.  action[e] < 0 = "reset step": only simulate opponents up to the learner's first turn (SplendorEnv.reset).
  * reward[e] int8, terminated[e] u8 (end kind), illegal[e] u8, mask [N][110] u32, obs [N][265] f32 (mask/obs optional). */
-int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const int8_t *learner,
-                 const int16_t *action, int8_t *reward, uint8_t *terminated, uint8_t *illegal, uint32_t *mask,
-                 float *obs, int64_t N, int P, uint32_t flags, void *stream);
+int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
+                 const int8_t *learner, const int16_t *action, int8_t *reward, uint8_t *terminated, uint8_t *illegal,
+                 uint32_t *mask, float *obs, int64_t N, int P, uint32_t flags, void *stream);
 
 /* Host-buffer forms (the end-to-end path a reference-side caller uses): pageable or pinned HOST pointers in and out,
  * device staging buffers owned by the library, copies + kernel + copies on `stream`, then a stream synchronise.

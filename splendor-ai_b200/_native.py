@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libsplendor_b200.so")
+LIB_PATH = os.environ.get("SPL_LIB") or os.path.join(CSRC, "libsplendor_b200.so")  # SPL_LIB: A/B a variant build
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
@@ -71,15 +71,15 @@ def lib():
         L.spl_state_words.argtypes = [i32]
         L.spl_error_string.argtypes = [i32]
         L.spl_error_string.restype = C.c_char_p
-        L.spl_reset.argtypes = [vp, u64, u64, i64, i32, vp, vp, vp]
+        L.spl_reset.argtypes = [vp, u64, u64, vp, vp, i64, i32, vp, vp, vp]
         L.spl_inject.argtypes = [vp, vp, vp, i64, i32, vp]
         L.spl_legal_mask.argtypes = [vp, vp, i64, i32, vp]
-        L.spl_step.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, i64, i32, u32, vp]
+        L.spl_step.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, i64, i32, u32, vp]
         L.spl_final_scores.argtypes = [vp, vp, vp, vp, i64, i32, u32, vp]
         L.spl_observe.argtypes = [vp, vp, vp, i64, i32, vp]
         L.spl_playout.argtypes = [u64, u64, i64, i32, u32, i32, vp, vp, vp, vp, vp, i32, vp, vp]
-        L.spl_playout_from.argtypes = [vp, vp, u64, u64, i64, i32, u32, i32, vp, vp, vp, vp, vp, i32, vp]
-        L.spl_env_step.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, i64, i32, u32, vp]
+        L.spl_playout_from.argtypes = [vp, vp, u64, u64, vp, i64, i32, u32, i32, vp, vp, vp, vp, vp, i32, vp]
+        L.spl_env_step.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, u32, vp]
         L.spl_playout_host.argtypes = [vp, vp, u64, u64, i64, i32, u32, i32, vp, vp, vp, vp, vp]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = the .so does not match include/splendor_b200.h

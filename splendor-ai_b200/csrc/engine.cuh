@@ -200,13 +200,8 @@ __device__ __forceinline__ uint32_t occupied4(uint32_t dealt_word)  // 4-bit mas
     return ((((~dealt_word) & 0x80808080u) >> 7) * 0x00204081u) >> 21 & 15u;
 }
 
-// Out of line by default: ~70 instructions called from the action draw, every deal and the reset; inlining all call
-// sites made the playout kernel overflow the instruction cache (profiles/r1a).
-#ifndef SPL_PHILOX_INLINE
-#define SPL_PHILOX_INLINE __noinline__
-#endif
 // Philox4x32-10 (Salmon et al. 2011).  counter = (game lo, game hi, index, stream), key = seed.
-__device__ SPL_PHILOX_INLINE uint4 philox(uint64_t seed, uint64_t game, uint32_t index, uint32_t stream)
+__device__ __forceinline__ uint4 philox_inline(uint64_t seed, uint64_t game, uint32_t index, uint32_t stream)
 {
     uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = index, c3 = stream;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -218,6 +213,13 @@ __device__ SPL_PHILOX_INLINE uint4 philox(uint64_t seed, uint64_t game, uint32_t
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
+}
+// Out-of-line copy for the rare call sites (every deal, the reset): inlining all of them made the playout kernel
+// overflow the instruction cache (profiles/r1a: no_instruction stalls).  The per-step action draw uses the inline
+// form so that its 10-round dependent chain overlaps the branch-free counting code.
+__device__ __noinline__ uint4 philox(uint64_t seed, uint64_t game, uint32_t index, uint32_t stream)
+{
+    return philox_inline(seed, game, index, stream);
 }
 enum Stream { STREAM_ACTION = 0, STREAM_DECK0 = 1, STREAM_NOBLES = 4, STREAM_ENV = 5 };
 

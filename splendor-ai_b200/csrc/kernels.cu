@@ -36,13 +36,13 @@ static_assert(sizeof(Tables) % 4 == 0, "Tables must be word-copyable");
 
 // ---------------------------------------------------------------------------------------------- reset / inject
 template <int P>
-__global__ void __launch_bounds__(BLOCK) reset_kernel(uint4 *state, uint64_t seed, uint64_t first_game, int64_t N,
-                                                      uint8_t *deck_lists_out, uint8_t *nobles_out)
+__global__ void __launch_bounds__(BLOCK) reset_kernel(uint4 *state, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
+                                                      const uint8_t *where, int64_t N, uint8_t *deck_lists_out, uint8_t *nobles_out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= N || (where && !where[i])) return;
     Env<P> e;
-    const uint64_t game = first_game + (uint64_t)i;
+    const uint64_t game = game_ids ? game_ids[i] : first_game + (uint64_t)i;
     reset_env(e, seed, game);
     store_env(e, state, N, i);
     if (nobles_out)
@@ -91,6 +91,7 @@ struct PlayoutArgs {
     uint4 *state;           // FRESH: optional final-state output; else in/out states
     const uint8_t *decks;   // explicit deck lists (only with states) or nullptr
     uint64_t seed, first_game;
+    const uint64_t *game_ids;  // per-game ids (only with states) or nullptr = first_game + index
     int64_t n_games;
     uint32_t flags;
     int max_steps;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(BLOCK) playout_kernel(const PlayoutArgs a)
     while (!__all_sync(0xFFFFFFFFu, done)) {
         if (!done) {
             if (!have) {  // next game of this lane
-                src.game = a.first_game + (uint64_t)g;
+                src.game = (!FRESH && a.game_ids) ? a.game_ids[g] : a.first_game + (uint64_t)g;
                 if (FRESH) reset_env(e, a.seed, src.game);
                 else {
                     load_env(e, a.state, a.n_games, g);
@@ -145,9 +146,9 @@ __global__ void __launch_bounds__(BLOCK) playout_kernel(const PlayoutArgs a)
                 Ctx c;
                 FamilyCounts f;
                 Choice ch;
+                const uint32_t r = philox_inline(a.seed, src.game, (uint32_t)t, STREAM_ACTION).x;
                 make_ctx(e, sT, c);
                 const int total = count_legal(e, sT, c, f);
-                const uint32_t r = philox(a.seed, src.game, (uint32_t)t, STREAM_ACTION).x;
                 select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
                 if (a.trace && t < a.trace_len) a.trace[(int64_t)t * a.n_games + g] = (int16_t)ch.idx;
                 apply_action(e, ch, src);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(BLOCK) playout_kernel(const PlayoutArgs a)
 // ---------------------------------------------------------------------------------------------- step
 template <int P>
 __global__ void __launch_bounds__(BLOCK) step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
-                                                     const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal,
+                                                     const uint64_t *game_ids, const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal,
                                                      int64_t N, uint32_t flags)
 {
     __shared__ Tables sT;
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(uint4 *state, const uint8_t
         Choice ch;
         make_ctx(e, sT, c);
         if (decode_and_check(e, sT, c, a, ch)) {
-            const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, first_game + (uint64_t)i};
+            const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
             rew = apply_action(e, ch, src);
         } else {
             bad = 1;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(BLOCK) observe_kernel(const uint4 *state, cons
 // Phase 2 (warp per env, state handed over through shared memory): the learner's next mask and observation.
 template <int P>
 __global__ void __launch_bounds__(BLOCK) env_step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
-                                                         const int8_t *learner, const int16_t *action, int8_t *reward,
+                                                         const uint64_t *game_ids, const int8_t *learner, const int16_t *action, int8_t *reward,
                                                          uint8_t *terminated, uint8_t *illegal, uint32_t *mask, float *obs,
                                                          int64_t N, uint32_t flags)
 {
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(uint4 *state, const uin
         Env<P> e;
         load_env(e, state, N, i);
         const int me = learner[i], a = action[i];
-        const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, first_game + (uint64_t)i};
+        const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
         int rew = 0, bad = 0;
         bool go = true;
         if (a >= 0) {
@@ -440,14 +441,14 @@ int spl_warmup(void)
     return SPL_OK;
 }
 
-int spl_reset(void *state, uint64_t seed, uint64_t first_game, int64_t N, int P, uint8_t *deck_lists_out,
-              uint8_t *nobles_out, void *stream)
+int spl_reset(void *state, uint64_t seed, uint64_t first_game, const uint64_t *game_ids, const uint8_t *where, int64_t N, int P,
+              uint8_t *deck_lists_out, uint8_t *nobles_out, void *stream)
 {
     if (!state || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
     DISPATCH_P(P, reset_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
-                      (uint4 *)state, seed, first_game, N, deck_lists_out, nobles_out));
+                      (uint4 *)state, seed, first_game, game_ids, where, N, deck_lists_out, nobles_out));
     CK(cudaGetLastError());
     return SPL_OK;
 }
@@ -474,14 +475,14 @@ int spl_legal_mask(const void *state, uint32_t *mask, int64_t N, int P, void *st
     return SPL_OK;
 }
 
-int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const int16_t *action, int8_t *reward,
-             uint8_t *done, uint8_t *illegal, int64_t N, int P, uint32_t flags, void *stream)
+int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids, const int16_t *action,
+             int8_t *reward, uint8_t *done, uint8_t *illegal, int64_t N, int P, uint32_t flags, void *stream)
 {
     if (!state || !action || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
     DISPATCH_P(P, step_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
-                      (uint4 *)state, decks, seed, first_game, action, reward, done, illegal, N, flags));
+                      (uint4 *)state, decks, seed, first_game, game_ids, action, reward, done, illegal, N, flags));
     CK(cudaGetLastError());
     return SPL_OK;
 }
@@ -530,32 +531,32 @@ int spl_playout(uint64_t seed, uint64_t first_game, int64_t num_games, int P, ui
     if (num_games < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (num_games == 0) return SPL_OK;
-    PlayoutArgs a{(uint4 *)final_state, nullptr, seed, first_game, num_games, flags, max_steps, score2, steps, end_kind,
+    PlayoutArgs a{(uint4 *)final_state, nullptr, seed, first_game, nullptr, num_games, flags, max_steps, score2, steps, end_kind,
                   (unsigned long long *)counters, trace, trace_len};
     return launch_playout(true, a, P, (cudaStream_t)stream);
 }
 
-int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, int64_t N, int P, uint32_t flags,
-                     int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind, int64_t *counters, int16_t *trace,
+int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids, int64_t N,
+                     int P, uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind, int64_t *counters, int16_t *trace,
                      int trace_len, void *stream)
 {
     if (!state || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    PlayoutArgs a{(uint4 *)state, decks, seed, first_game, N, flags, max_steps, score2, steps, end_kind,
+    PlayoutArgs a{(uint4 *)state, decks, seed, first_game, game_ids, N, flags, max_steps, score2, steps, end_kind,
                   (unsigned long long *)counters, trace, trace_len};
     return launch_playout(false, a, P, (cudaStream_t)stream);
 }
 
-int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const int8_t *learner,
-                 const int16_t *action, int8_t *reward, uint8_t *terminated, uint8_t *illegal, uint32_t *mask, float *obs,
+int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
+                 const int8_t *learner, const int16_t *action, int8_t *reward, uint8_t *terminated, uint8_t *illegal, uint32_t *mask, float *obs,
                  int64_t N, int P, uint32_t flags, void *stream)
 {
     if (!state || !learner || !action || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
     DISPATCH_P(P, env_step_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
-                      (uint4 *)state, decks, seed, first_game, learner, action, reward, terminated, illegal, mask, obs, N, flags));
+                      (uint4 *)state, decks, seed, first_game, game_ids, learner, action, reward, terminated, illegal, mask, obs, N, flags));
     CK(cudaGetLastError());
     return SPL_OK;
 }
@@ -599,7 +600,7 @@ int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t 
     CK(cudaMemcpyAsync(b + o_nobles, nobles, (size_t)N * 5, cudaMemcpyHostToDevice, stream));
     CK(cudaMemsetAsync(b + o_ctr, 0, 128, stream));
     if (int rc = spl_inject(b + o_state, (const uint8_t *)(b + o_decks), (const uint8_t *)(b + o_nobles), N, P, stream)) return rc;
-    if (int rc = spl_playout_from(b + o_state, (const uint8_t *)(b + o_decks), seed, first_game, N, P, flags, max_steps,
+    if (int rc = spl_playout_from(b + o_state, (const uint8_t *)(b + o_decks), seed, first_game, nullptr, N, P, flags, max_steps,
                                   (int8_t *)(b + o_score), (int16_t *)(b + o_steps), (uint8_t *)(b + o_kind),
                                   (int64_t *)(b + o_ctr), nullptr, 0, stream))
         return rc;

@@ -47,19 +47,28 @@ class BatchedSplendor:
         self.flags = nat.F_LIMIT_ROUNDS if limit_rounds else 0
         self.state = torch.zeros(state_shape(self.N, self.P), dtype=torch.int32, device=self.device)
         self.decks = None  # explicit deck lists [N, 90] uint8 after inject()
+        self.game_ids = None  # per-env game ids (int64 [N]) once envs are reset individually; None = first_game + index
         self.reset()
 
     # -- construction -------------------------------------------------------------------------------------------
-    def reset(self, first_game: int | None = None, want_lists: bool = False):
-        """SplendorGameRule(P).initialGameState() for every env (counter-based decks)."""
+    def reset(self, first_game: int | None = None, want_lists: bool = False, where: torch.Tensor | None = None,
+              game_ids: torch.Tensor | None = None):
+        """SplendorGameRule(P).initialGameState() for every env (counter-based decks), or only for envs with where != 0.
+
+        game_ids (int64 [N]): per-env game ids; once given they are used by every later call on this batch."""
         if first_game is not None:
             self.first_game = int(first_game)
+        if game_ids is not None:
+            self.game_ids = game_ids.to(device=self.device, dtype=torch.int64).contiguous()
+        elif where is None:
+            self.game_ids = None
+        w = None if where is None else where.to(device=self.device, dtype=torch.uint8).contiguous()
         self.decks = None
         lists = torch.empty((self.N, 90), dtype=torch.uint8, device=self.device) if want_lists else None
         nobles = torch.empty((self.N, 5), dtype=torch.uint8, device=self.device) if want_lists else None
         with torch.cuda.device(self.device):
-            nat.check(self.lib.spl_reset(_ptr(self.state), self.seed, self.first_game, self.N, self.P, _ptr(lists),
-                                         _ptr(nobles), _stream(self.device)), "spl_reset")
+            nat.check(self.lib.spl_reset(_ptr(self.state), self.seed, self.first_game, _ptr(self.game_ids), _ptr(w), self.N, self.P,
+                                         _ptr(lists), _ptr(nobles), _stream(self.device)), "spl_reset")
         return (lists, nobles) if want_lists else None
 
     def inject(self, deck_lists, nobles):
@@ -89,7 +98,7 @@ class BatchedSplendor:
         done = torch.empty(self.N, dtype=torch.uint8, device=self.device)
         illegal = torch.empty(self.N, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            nat.check(self.lib.spl_step(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, _ptr(a), _ptr(reward),
+            nat.check(self.lib.spl_step(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, _ptr(self.game_ids), _ptr(a), _ptr(reward),
                                         _ptr(done), _ptr(illegal), self.N, self.P, self.flags, _stream(self.device)), "spl_step")
         return reward, done, illegal
 
@@ -121,7 +130,7 @@ class BatchedSplendor:
             trace=torch.empty((trace_len, self.N), dtype=torch.int16, device=self.device) if trace_len else None,
         )
         with torch.cuda.device(self.device):
-            nat.check(self.lib.spl_playout_from(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, self.N, self.P,
+            nat.check(self.lib.spl_playout_from(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, _ptr(self.game_ids), self.N, self.P,
                                                 self.flags, max_steps, _ptr(out["score2"]), _ptr(out["steps"]),
                                                 _ptr(out["end_kind"]), _ptr(out["counters"]), _ptr(out["trace"]), trace_len,
                                                 _stream(self.device)), "spl_playout_from")
@@ -137,7 +146,7 @@ class BatchedSplendor:
         mask = torch.empty((self.N, MASK_WORDS), dtype=torch.int32, device=self.device) if want_mask else None
         obs = torch.empty((self.N, OBS_SIZE), dtype=torch.float32, device=self.device) if want_obs else None
         with torch.cuda.device(self.device):
-            nat.check(self.lib.spl_env_step(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, _ptr(l), _ptr(a),
+            nat.check(self.lib.spl_env_step(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, _ptr(self.game_ids), _ptr(l), _ptr(a),
                                             _ptr(reward), _ptr(term), _ptr(illegal), _ptr(mask), _ptr(obs), self.N, self.P,
                                             self.flags, _stream(self.device)), "spl_env_step")
         return obs, reward, term, illegal, mask

@@ -65,6 +65,18 @@ class AgentTrace:
         self.action_reward = []
 
 
+def draw_initial_decks(num_agents):
+    """BoardState.__init__ (splendor_model.py:83-90) restated on ids: sample the nobles first, then shuffle tier 1, 2, 3 -
+    the same `random` calls on lists of the same lengths, hence the same game as the reference for the same seed."""
+    nobles = random.sample(range(len(NOBLES)), k=num_agents + 1)
+    lists = []
+    for t in range(3):
+        deck = list(range(TIER_BASE[t], TIER_BASE[t] + TIER_SIZE[t]))
+        random.shuffle(deck)
+        lists += deck
+    return lists, nobles
+
+
 class SplendorState(template.GameState):
     """The reference's object graph, decoded from the packed state words."""
 
@@ -79,14 +91,7 @@ class SplendorState(template.GameState):
 
         self.num_agents = num_agents
         if _deck_lists is None:
-            # BoardState.__init__ (:83-90): sample the nobles first, then shuffle tier 1, 2, 3 - same `random` calls
-            _nobles = random.sample(range(len(NOBLES)), k=num_agents + 1)
-            lists = []
-            for t in range(3):
-                deck = list(range(TIER_BASE[t], TIER_BASE[t] + TIER_SIZE[t]))
-                random.shuffle(deck)
-                lists += deck
-            _deck_lists = lists
+            _deck_lists, _nobles = draw_initial_decks(num_agents)
         self._deck_lists = np.asarray(_deck_lists, np.uint8)
         self._words = _single.inject(num_agents, self._deck_lists, _nobles)
         self._bought = [{c: [] for c in COLOURS.values()} for _ in range(num_agents)]
