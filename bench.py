@@ -20,6 +20,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
 
 GAMES_PER_GPU = 65_536
 PLAYERS = 2
@@ -164,10 +165,10 @@ def run_b200(args):
     import splendor_ai_b200 as pkg
     from splendor_ai_b200 import dist as D
 
-    rank, local_rank, world = D.init()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
+    torch.cuda.set_device(D.world()[1])
+    rank, local_rank, world = D.init()
     dev = torch.device("cuda", local_rank)
     pkg.build()
     lib = pkg._native.lib()
@@ -240,6 +241,8 @@ def run_b200(args):
     D.allreduce_counters(e2e_steps)
     e2e_value = int(e2e_steps.item()) / e2e_s
 
+    D.barrier()
+    D.shutdown()
     if rank != 0:
         return
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
