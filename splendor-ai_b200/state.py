@@ -122,3 +122,41 @@ def snapshots(words: np.ndarray, P: int) -> np.ndarray:
 def remaining_deck_sets(deck_masks_row) -> list:
     """Counter-based decks: per tier, the sorted card ids still in the deck (from one env's deck_masks)."""
     return [[TIER_BASE[t] + i for i in range(TIER_SIZE[t]) if (int(deck_masks_row[t]) >> i) & 1] for t in range(3)]
+
+
+def _g6_word(counts: np.ndarray) -> np.ndarray:
+    """[..., 6] (or 5) counts by colour id -> g6 word."""
+    w = np.zeros(counts.shape[:-1], np.uint32)
+    for cid in range(counts.shape[-1]):
+        w |= counts[..., cid].astype(np.uint32) << np.uint32(5 * FIELD_OF_COLOUR_ID[cid])
+    return w
+
+
+def pack(fields: dict, P: int, deck_lists: np.ndarray | None = None):
+    """Inverse of `unpack` for EXPLICIT-deck states: field arrays (leading dimension N; keys bank, dealt, nobles, deck_n,
+    cur, gems, cards, resv, score, passed, turns, nobles_mask) -> packed words [C, N, 4] uint32.  The deck lists ([N,90],
+    reference list order) are not part of the words; they are passed to the kernels separately."""
+    N = np.asarray(fields["bank"]).shape[0]
+    words = np.zeros((state_words(P) // 4, N, 4), np.uint32)
+    words[0, :, 0] = _g6_word(np.asarray(fields["bank"]))
+    dealt = np.asarray(fields["dealt"], np.uint32)
+    for t in range(3):
+        words[0, :, 1 + t] = dealt[:, 4 * t] | dealt[:, 4 * t + 1] << 8 | dealt[:, 4 * t + 2] << 16 | dealt[:, 4 * t + 3] << 24
+    dn = np.asarray(fields["deck_n"], np.uint32)
+    words[1, :, 0] = dn[:, 0] | dn[:, 1] << 8 | dn[:, 2] << 16
+    nob = np.asarray(fields["nobles"], np.uint32).copy()
+    nob[nob == NONE] = 15
+    meta = np.zeros(N, np.uint32)
+    for k in range(5):
+        meta |= (nob[:, k] & 15) << np.uint32(4 * k)
+    meta |= np.asarray(fields["cur"], np.uint32) << 20
+    meta |= np.uint32((P - 2) << 22) | np.uint32(META_EXPLICIT)
+    words[1, :, 3] = meta
+    for p in range(P):
+        words[2 + p, :, 0] = _g6_word(np.asarray(fields["gems"])[:, p])
+        words[2 + p, :, 1] = _g6_word(np.asarray(fields["cards"])[:, p])
+        rv = np.asarray(fields["resv"], np.uint32)[:, p]
+        words[2 + p, :, 2] = rv[:, 0] | rv[:, 1] << 8 | rv[:, 2] << 16 | np.asarray(fields["score"], np.uint32)[:, p] << 24
+        words[2 + p, :, 3] = (np.asarray(fields["turns"], np.uint32)[:, p] & 0xFFFF) | \
+            (np.asarray(fields["nobles_mask"], np.uint32)[:, p] & 0x3FF) << 16 | (np.asarray(fields["passed"], np.uint32)[:, p] & 1) << 26
+    return words

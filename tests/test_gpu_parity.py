@@ -255,3 +255,40 @@ def test_host_buffer_abi_call(pkg, oracle):
     assert rc == 0, pkg._native.lib().spl_error_string(rc)
     sc, st, c = oracle.playout_many(seed, 0, N, P, False, 1000, nthreads=os.cpu_count() or 1)
     assert np.array_equal(score2, sc) and np.array_equal(steps.astype(np.int32), st) and np.array_equal(ctr, c)
+
+
+@pytest.mark.parametrize("P", [2, 3, 4])
+def test_fuzzed_states_on_gpu(pkg, oracle, P):
+    """Arbitrary hand-built states (tests/fuzz_states.py: 10-gem holders, drained banks, empty slots/decks, 7-card cap,
+    3 reserved, several nobles earned, pass-only, 100-turn cap) packed into the device layout: mask, observation for
+    every seat, gameEnds/calScore, and the successor of one sampled legal action per env - all vs the oracle."""
+    from fuzz_states import random_state
+
+    N, rng = 3000, np.random.default_rng(100 + P)
+    orcs, fields, lists = [], [], []
+    for _ in range(N):
+        o, f, l = random_state(rng, oracle, P)
+        orcs.append(o); fields.append(f); lists.append(l)
+    merged = {k: np.concatenate([f[k] for f in fields]) for k in fields[0]}
+    for limit in (False, True):
+        eng = pkg.BatchedSplendor(N, P, limit_rounds=limit)
+        eng.state.copy_(torch.from_numpy(pkg.state.pack(merged, P).view(np.int32)))
+        eng.decks = torch.from_numpy(np.stack(lists)).to(eng.device)
+        assert np.array_equal(snaps(eng, pkg), np.stack([o.snapshot() for o in orcs]))
+        mask = eng.legal_mask().cpu().numpy()
+        score2, outcome, kind = (x.cpu().numpy() for x in eng.final_scores())
+        obs = [eng.observe(torch.full((N,), s, dtype=torch.int8)).cpu().numpy() for s in range(P)]
+        act = np.zeros(N, np.int16)
+        for e, o in enumerate(orcs):
+            legal = oracle.legal(o)
+            assert np.array_equal(unpack_mask(mask[e]), legal), (P, e)
+            assert kind[e] == oracle.game_ends(o, limit) and list(score2[e]) == [oracle.cal_score2(o, i) for i in range(P)], (P, e)
+            for s in range(P):
+                assert np.array_equal(obs[s][e].view(np.uint32), oracle.observe(o, s).view(np.uint32)), (P, e, s)
+            act[e] = rng.choice(legal)
+        reward, done, illegal = (x.cpu().numpy() for x in eng.step(torch.from_numpy(act)))
+        sn = snaps(eng, pkg)
+        for e, o in enumerate(orcs):
+            o2 = o.copy()
+            assert illegal[e] == 0 and reward[e] == oracle.step(o2, int(act[e])), (P, e)
+            assert done[e] == oracle.game_ends(o2, limit) and np.array_equal(sn[e], o2.snapshot()), (P, e)
