@@ -770,110 +770,168 @@ __device__ __forceinline__ void final_scores(const Env<P> &e, int (&score2)[P], 
     for (int p = 0; p < P; p++) outcome[p] = score2[p] == best ? (nbest > 1 ? 1 : 2) : 0;
 }
 
-// ------------------------------------------------------------------------------------------------ warp-per-env pieces
-// The legal-action MASK and the OBSERVATION are produced by one warp per env; these are the per-lane bodies (the
-// kernels add the warp synchronisation, the ballot for "nothing legal -> pass" and the coalesced stores).
-constexpr int MASK_PAD = 112;
-constexpr int OBS_PAD = 272;
+// ------------------------------------------------------------------------------------------------ mask + observation
+// The legal-action MASK (3510 bits) and the OBSERVATION (265 floats) are built by ONE THREAD PER ENV into its own row of
+// a shared-memory tile, which the block then stores to HBM coalesced (kernels.cu).  A first version used one warp per
+// env; it spent ~500-800 warp-instructions per env with most lanes idle and reached only 6-7 % of HBM bandwidth
+// (profiles/r1_kernels.md), so the rule work moved to one thread and only the data movement stays cooperative.
+constexpr int MASK_ROW = 113;  // words per thread row: 110 used, odd stride (bank spread), 3 spare for or_bits' overhang
+constexpr int OBS_ROW = 265;   // floats per thread row (265 is odd: conflict-free across lanes as is)
 
-__device__ __forceinline__ void set_bit(uint32_t *m, int idx) { atomicOr(&m[idx >> 5], 1u << (idx & 31)); }
-
-// Sets one bit per noble slot: base + n*stride for n in (S ? {k+1 : k in S} : {0})
-__device__ __forceinline__ void set_for_nobles(uint32_t *m, int base, int stride, uint32_t S)
+// OR a bit pattern into the row at an arbitrary bit offset (row zeroed beforehand; plain read-modify-write: the row is
+// private to the thread)
+__device__ __forceinline__ void or_bits64(uint32_t *m, int start, uint64_t pat)
 {
-    if (S == 0) { set_bit(m, base); return; }
-    for (uint32_t s = S; s; s &= s - 1) set_bit(m, base + __ffs(s) * stride);
+    const int w = start >> 5, sh = start & 31;
+    const uint64_t lo = pat << sh;
+    m[w] |= (uint32_t)lo;
+    m[w + 1] |= (uint32_t)(lo >> 32);
+    m[w + 2] |= sh ? (uint32_t)(pat >> (64 - sh)) : 0u;
+}
+__device__ __forceinline__ void or_bits32(uint32_t *m, int start, uint32_t pat)
+{
+    const int w = start >> 5, sh = start & 31;
+    const uint64_t lo = (uint64_t)pat << sh;
+    m[w] |= (uint32_t)lo;
+    m[w + 1] |= (uint32_t)(lo >> 32);
+}
+// variants x three noble slots: bit (n*V + v) for every v in `variants` and n in the low 3 bits of `slots`
+__device__ __forceinline__ uint64_t times_nobles(uint32_t variants, int V, uint32_t slots)
+{
+    const uint64_t v = variants;
+    return ((slots & 1u) ? v : 0ull) | ((slots & 2u) ? v << V : 0ull) | ((slots & 4u) ? v << (2 * V) : 0ull);
+}
+// bits of the variants in [v0, v1) of a returned-gems row that the agent can actually pay
+__device__ __forceinline__ uint32_t feasible_bits(const uint32_t *row, int v0, int v1, uint32_t gems)
+{
+    uint32_t bits = 0;
+    for (int v = v0; v < v1; v++) bits |= satsub6(row[v], gems) == 0 ? 1u << v : 0u;
+    return bits;
 }
 
-// Lane `lane` of the warp that owns env e sets its share of the 3510 mask bits in m (zeroed, >= 110 words, shared
-// memory).  Returns whether it set anything; if no lane did, the caller sets the pass bits (set_for_nobles(m,0,1,S)).
+// getLegalActions + create_legal_actions_mask (splendor_model.py:404-576, gym/envs/utils.py:148-164) for the seat to move,
+// OR-ed into the zeroed row m.  Noble slots: NP has bit n set for every noble slot n the action may carry.
 template <int P>
-__device__ __forceinline__ bool lane_fill_mask(const Env<P> &e, const Tables &T, const Ctx &c, uint32_t *m, int lane)
+__device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &T, const Ctx &c, uint32_t *m)
 {
+    const uint32_t NP = c.S ? c.S << 1 : 1u;
     bool any = false;
-    // reserve: lane = board slot (:498-520)
-    if (lane < 12 && c.n_resv < 3 && (c.occ >> lane & 1)) {
-        const int base = BASE_RESERVE + lane * 42;
-        if (!c.bank_yellow) set_for_nobles(m, base, 7, c.S);
-        else if (c.hold < 10) set_for_nobles(m, base + 1, 7, c.S);
-        else
-            for (int n = 0; n < 5; n++)
-                if (c.h1 >> field_of_normal(n) & 1) set_for_nobles(m, base + 2 + n, 7, c.S);
-        any = true;
-    }
-    // collect_same: lanes 12..16 = colour (:475-496)
-    if (lane >= 12 && lane < 17) {
-        const int col = lane - 12, fl = field_of_normal(col), e2 = c.hold - 8;
-        if (c.A4 >> fl & 1) {
-            const uint32_t *row = T.ret_same + col * 21;
-            const int base = BASE_SAME + col * 126;
-            if (e2 <= 0) { set_for_nobles(m, base, 21, c.S); any = true; }
-            else
-                for (int v = 1; v < 21; v++)
-                    if ((int)hsum6(row[v]) == e2 && satsub6(row[v], c.gems) == 0) { set_for_nobles(m, base + v, 21, c.S); any = true; }
-        }
-    }
-    // collect_diff: lane = colour combination (:437-473)
-    if (lane < 25) {
-        const int L = combo_len(lane), V = L == 1 ? 6 : (L == 2 ? 15 : 20), ex = c.hold + L - 10;
-        if (!(T.combo_mask[lane] & ~c.A1) && L >= c.Lmin) {
-            const uint32_t *row = T.ret_diff + T.combo_off[lane];
-            const int base = T.combo_base[lane];
-            if (ex <= 0) { set_for_nobles(m, base, V, c.S); any = true; }
-            else
-                for (int v = 1; v < V; v++)
-                    if ((int)hsum6(row[v]) == ex && satsub6(row[v], c.gems) == 0) { set_for_nobles(m, base + v, V, c.S); any = true; }
-        }
-    }
-    // buy: lanes 17..31 = 12 board slots + 3 reserved cards (:522-568)
-    if (lane >= 17) {
-        const int s = lane - 17;
-        uint32_t w = s < 4 ? e.d[0] : (s < 8 ? e.d[1] : (s < 12 ? e.d[2] : c.resv));
-        const uint32_t id = byte_of(w, s & 3);
-        uint32_t pay;
-        if (id != NONE8) {
-            const uint2 cw = T.card[id];
-            if (can_buy(c, cw, pay)) {
-                const uint32_t Sb = c.S | ((c.near >> (cw.y & 31u)) & 31u);
-                set_for_nobles(m, s < 12 ? BASE_BUY_AVAILABLE + s * 6 : BASE_BUY_RESERVE + (s - 12) * 6, 1, Sb);
-                any = true;
+    // reserve (:498-520): the same 42-bit (noble x variant) pattern for every occupied slot
+    if (c.n_resv < 3 && c.occ) {
+        uint32_t vr = 1u;
+        if (c.bank_yellow) {
+            vr = 2u;
+            if (c.hold >= 10) {
+                vr = 0;
+#pragma unroll
+                for (int n = 0; n < 5; n++) vr |= (c.h1 >> field_of_normal(n) & 1u) << (2 + n);
             }
         }
+        const uint64_t pat = times_nobles(vr, 7, NP) | times_nobles(vr, 7, NP >> 3) << 21;
+#pragma unroll 1
+        for (uint32_t occ = c.occ; occ; occ &= occ - 1) or_bits64(m, BASE_RESERVE + 42 * (__ffs(occ) - 1), pat);
+        any = true;
     }
-    return any;
+    // collect_same (:475-496)
+    {
+        const int e2 = c.hold - 8;
+#pragma unroll 1
+        for (int col = 0; col < 5; col++) {
+            const int fl = field_of_normal(col);
+            if (!(c.A4 >> fl & 1u)) continue;
+            const uint32_t *row = T.ret_same + col * 21;
+            const uint32_t vs = e2 <= 0 ? 1u : (e2 == 1 ? feasible_bits(row, 11, 16, c.gems)
+                                                        : feasible_bits(row, 1, 11, c.gems) | feasible_bits(row, 16, 21, c.gems));
+            if (!vs) continue;
+            or_bits64(m, BASE_SAME + 126 * col, times_nobles(vs, 21, NP));
+            if (NP >> 3) or_bits64(m, BASE_SAME + 126 * col + 63, times_nobles(vs, 21, NP >> 3));
+            any = true;
+        }
+    }
+    // collect_diff (:437-473)
+#pragma unroll 1
+    for (int ci = 0; ci < 25; ci++) {
+        const uint32_t cm = T.combo_mask[ci];
+        const int L = combo_len(ci);
+        if ((cm & ~c.A1) || L < c.Lmin) continue;
+        const int V = L == 1 ? 6 : (L == 2 ? 15 : 20), ex = c.hold + L - 10, kk = 6 - L;
+        const int r1 = 1 + kk, r2 = r1 + (kk * (kk + 1) >> 1);
+        const uint32_t *row = T.ret_diff + T.combo_off[ci];
+        const uint32_t vd = ex <= 0 ? 1u : (ex == 1 ? feasible_bits(row, 1, r1, c.gems)
+                                                    : (ex == 2 ? feasible_bits(row, r1, r2, c.gems) : feasible_bits(row, r2, V, c.gems)));
+        if (!vd) continue;
+        const int base = T.combo_base[ci];
+        or_bits64(m, base, times_nobles(vd, V, NP));
+        if (NP >> 3) or_bits64(m, base + 3 * V, times_nobles(vd, V, NP >> 3));
+        any = true;
+    }
+    // buy (:522-568): 6 noble bits per card; board slots 0-4 / 5-9 / 10-11 and the reserved cards as four 32-bit patterns
+    {
+        const uint32_t eff = (c.gems & ~(31u << YSH)) + c.cards;
+        const uint32_t cap = ((c.cards + 9u * ONES6) & H6) | (16u << YSH);
+        uint32_t b0 = 0, b1 = 0, b2 = 0, br = 0;
+#pragma unroll
+        for (int s = 0; s < 15; s++) {
+            const uint32_t w = s < 12 ? e.d[s >> 2] : c.resv;
+            const uint2 cw = T.card[(w >> (8 * (s & 3))) & 127u];
+            const uint32_t sh = cw.y & 31u;
+            const bool ok = hsum6_small(satsub6(cw.x, eff)) <= (uint32_t)c.yellow && !((cap >> sh) & 16u);
+            const uint32_t Sb = c.S | ((c.near >> sh) & 31u);
+            const uint32_t np = ok ? (Sb ? Sb << 1 : 1u) : 0u;
+            if (s < 5) b0 |= np << (6 * s);
+            else if (s < 10) b1 |= np << (6 * (s - 5));
+            else if (s < 12) b2 |= np << (6 * (s - 10));
+            else br |= np << (6 * (s - 12));
+        }
+        or_bits32(m, BASE_BUY_AVAILABLE, b0);
+        or_bits32(m, BASE_BUY_AVAILABLE + 30, b1);
+        or_bits32(m, BASE_BUY_AVAILABLE + 60, b2);
+        or_bits32(m, BASE_BUY_RESERVE, br);
+        any = any || (b0 | b1 | b2 | br);
+    }
+    if (!any) m[0] |= NP;  // pass, only when nothing else is legal (:570-574)
 }
 
-// features.extract_metrics_with_cards (features.py:214-310, :377-480) for `seat`, into o[0..264] (zeroed, shared memory).
-// Phase A: lanes 0..14 own one card each (12 board slots, then the 3 reserved slots) and publish (distance, colour)
-// in scratch[0..14]; the warp synchronises; phase B: lanes 16..20 own one board noble each, lane 24 the scalar metrics.
-template <int P>
-__device__ __forceinline__ void lane_fill_obs_cards(const Env<P> &e, const Tables &T, int seat, float *o, uint32_t *scratch, int lane)
+// insert d into the ascending 4-tuple held in the bytes of t (keeps the four smallest)
+__device__ __forceinline__ uint32_t insert_sorted4(uint32_t t, uint32_t d)
 {
-    if (lane >= 15) return;
-    uint32_t gems = e.pg[0], cards = e.pc[0], resv = e.pr[0];
+    const uint32_t a0 = t & 0xFFu, a1 = (t >> 8) & 0xFFu, a2 = (t >> 16) & 0xFFu, a3 = t >> 24;
+    const uint32_t t0 = min(a0, d), r0 = max(a0, d), t1 = min(a1, r0), r1 = max(a1, r0), t2 = min(a2, r1), r2 = max(a2, r1);
+    return t0 | t1 << 8 | t2 << 16 | min(a3, r2) << 24;
+}
+
+// features.extract_metrics_with_cards(state, seat).astype(float32) (features.py:214-310, :377-480) into the zeroed row o
+template <int P>
+__device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T, const uint32_t *log1p_bits, int seat, float *o)
+{
+    uint32_t gems = e.pg[0], cards = e.pc[0], resv = e.pr[0], pinfo = e.pi[0];
 #pragma unroll
     for (int p = 1; p < P; p++)
-        if (seat == p) { gems = e.pg[p]; cards = e.pc[p]; resv = e.pr[p]; }
+        if (seat == p) { gems = e.pg[p]; cards = e.pc[p]; resv = e.pr[p]; pinfo = e.pi[p]; }
     const uint32_t bp = (gems & ~(31u << YSH)) + cards;  // buying power per normal colour (features.py:65-74), <= 14
-    const int s = lane;
-    const uint32_t w = s < 4 ? e.d[0] : (s < 8 ? e.d[1] : (s < 12 ? e.d[2] : resv));
-    const uint32_t id = byte_of(w, s & 3);
-    uint32_t dist = 0, colour_shift = 31;  // 5*field of the card's colour, 31 = no card here
-    if (id != NONE8) {
+    // per colour, the four cheapest candidate cards (board + own reserve) by missing gems; absent ones count 14
+    // (MAX_CARD_GEMS_DIST_3, features.py:257-274) - exactly what "sorted distances, padded" needs for the nobles
+    uint32_t best[6] = {0x0E0E0E0Eu, 0x0E0E0E0Eu, 0x0E0E0E0Eu, 0x0E0E0E0Eu, 0x0E0E0E0Eu, 0x0E0E0E0Eu};
+#pragma unroll
+    for (int s = 0; s < 15; s++) {
+        const uint32_t w = s < 12 ? e.d[s >> 2] : resv;
+        const uint32_t id = (w >> (8 * (s & 3))) & 0xFFu;
+        if (id == NONE8) continue;
         const uint2 cw = T.card[id];
-        const uint32_t miss = satsub6(cw.x, bp);
-        const uint32_t sum = hsum6(miss);
+        const uint32_t miss = satsub6(cw.x, bp), sum = hsum6_small(miss), sh = cw.y & 31u;
         uint32_t mx = 0;
 #pragma unroll
         for (int f = 0; f < 6; f++) mx = max(mx, field(miss, 5 * f));
         const uint32_t turns = sum == 0 ? 0u : max((sum + 2u) / 3u, mx);  // features.py:124-135
-        dist = sum; colour_shift = cw.y & 31u;
         o[(s < 12 ? 30 : 54 - 12) + s] = (float)sum;
         o[(s < 12 ? 42 : 57 - 12) + s] = (float)turns;
+#pragma unroll
+        for (int f = 0; f < 6; f++)
+            if (f != 2 && sh == 5u * f) best[f] = insert_sorted4(best[f], sum);
         // vectorize_card (features.py:377-413): one-hot over sklearn's alphabetical categories black, blue, green, red,
-        // white, yellow; then the cost in alphabetical order black, blue, green, red, white; deck_id; points
+        // white, yellow; the cost in alphabetical order black, blue, green, red, white; deck_id; points
         float *v = o + 70 + 13 * s;
-        const int fld = (int)(colour_shift / 5u);  // 0 black 1 red 3 green 4 blue 5 white
+        const int fld = (int)(sh / 5u);  // 0 black 1 red 3 green 4 blue 5 white
         v[fld == 0 ? 0 : (fld == 1 ? 3 : (fld == 3 ? 2 : (fld == 4 ? 1 : 4)))] = 1.f;
         v[6] = (float)field(cw.x, 0);
         v[7] = (float)field(cw.x, 20);
@@ -883,71 +941,50 @@ __device__ __forceinline__ void lane_fill_obs_cards(const Env<P> &e, const Table
         v[11] = (float)(cw.y >> 8 & 3u);
         v[12] = (float)(cw.y >> 5 & 7u);
     }
-    scratch[s] = dist | colour_shift << 8;
-}
-
-template <int P>
-__device__ __forceinline__ void lane_fill_obs_rest(const Env<P> &e, const Tables &T, const uint32_t *log1p_bits, int seat,
-                                                   float *o, const uint32_t *scratch, int lane)
-{
-    uint32_t gems = e.pg[0], cards = e.pc[0], resv = e.pr[0], pinfo = e.pi[0];
-#pragma unroll
-    for (int p = 1; p < P; p++)
-        if (seat == p) { gems = e.pg[p]; cards = e.pc[p]; resv = e.pr[p]; pinfo = e.pi[p]; }
-    if (lane >= 16 && lane < 21) {  // distance to one board noble (features.py:257-274)
-        const int k = lane - 16;
+    // distance to each board noble (features.py:257-274)
+#pragma unroll 1
+    for (int k = 0; k < 5; k++) {
         const uint32_t id = (e.meta >> (4 * k)) & 15u;
-        if (id != 15u) {
-            const uint32_t missing = satsub6(T.noble[id], cards);
-            int dist_gems = 0;
-            uint32_t used = 0;
-            for (int f = 0; f < 6; f++) {
-                const int cnt = (int)field(missing, 5 * f);
-                for (int it = 0; it < cnt; it++) {  // the cnt cheapest candidate cards of this colour, 14 per absent one
-                    int best = 255, bj = -1;
-                    for (int j = 0; j < 15; j++) {
-                        const uint32_t sj = scratch[j];
-                        if ((sj >> 8) == (uint32_t)(5 * f) && !(used >> j & 1) && (int)(sj & 0xFFu) < best) {
-                            best = (int)(sj & 0xFFu); bj = j;
-                        }
-                    }
-                    if (bj >= 0) used |= 1u << bj;
-                    dist_gems += bj >= 0 ? best : 14;
-                }
-            }
-            o[60 + k] = (float)dist_gems;
-            o[65 + k] = (float)hsum6(missing);
+        if (id == 15u) continue;
+        const uint32_t missing = satsub6(T.noble[id], cards);
+        uint32_t dist = 0;
+#pragma unroll
+        for (int f = 0; f < 6; f++) {
+            if (f == 2) continue;
+            const uint32_t cnt = field(missing, 5 * f), t = best[f];
+            dist += (cnt >= 1 ? t & 0xFFu : 0u) + (cnt >= 2 ? (t >> 8) & 0xFFu : 0u) + (cnt >= 3 ? (t >> 16) & 0xFFu : 0u) +
+                    (cnt >= 4 ? t >> 24 : 0u);
         }
+        o[60 + k] = (float)dist;
+        o[65 + k] = (float)hsum6_small(missing);
     }
-    if (lane == 24) {  // the scalar metrics (features.py:284-299)
-        const uint32_t bp = (gems & ~(31u << YSH)) + cards;
-        const uint32_t score = resv >> 24;
-        o[0] = 1.f;
-        o[1] = (float)(pinfo & 0xFFFFu);
-        o[2] = (float)score;
-        o[3] = score >= 15u ? 1.f : 0.f;
-        o[4] = (float)hsum6(cards);
-        o[5] = (float)__popc(~resv & 0x00808080u);
-        int s1 = 0, s2 = 0;
+    // the scalar metrics (features.py:284-299)
+    const uint32_t score = resv >> 24;
+    o[0] = 1.f;
+    o[1] = (float)(pinfo & 0xFFFFu);
+    o[2] = (float)score;
+    o[3] = score >= 15u ? 1.f : 0.f;
+    o[4] = (float)hsum6(cards);
+    o[5] = (float)__popc(~resv & 0x00808080u);
+    int s1 = 0, s2 = 0;
 #pragma unroll
-        for (int n = 0; n < 5; n++) {
-            const int sh = 5 * field_of_normal(n);
-            const int b = (int)field(bp, sh);
-            s1 += b; s2 += b * b;
-            o[9 + n] = (float)field(cards, sh);
-            o[14 + n] = (float)b;
-            o[19 + n] = __uint_as_float(log1p_bits[b]);
-        }
-        // np.var of five small integers = (5*sum(x^2) - sum(x)^2) / 25; numerator < 2^24, IEEE division: exact rounding
-        o[6] = __fdiv_rn((float)(5 * s2 - s1 * s1), 25.0f);
-        o[7] = (float)field(gems, YSH);
-        o[8] = (float)hsum6(gems);
+    for (int n = 0; n < 5; n++) {
+        const int sh = 5 * field_of_normal(n);
+        const int b = (int)field(bp, sh);
+        s1 += b; s2 += b * b;
+        o[9 + n] = (float)field(cards, sh);
+        o[14 + n] = (float)b;
+        o[19 + n] = __uint_as_float(log1p_bits[b]);
+    }
+    // np.var of five small integers = (5*sum(x^2) - sum(x)^2) / 25; numerator < 2^24, IEEE division: exact rounding
+    o[6] = __fdiv_rn((float)(5 * s2 - s1 * s1), 25.0f);
+    o[7] = (float)field(gems, YSH);
+    o[8] = (float)hsum6(gems);
 #pragma unroll
-        for (int p = 0; p < P; p++) {  // features.py:276-282, its i-1 indexing quirk kept
-            const float sc = (float)(e.pr[p] >> 24);
-            if (p < seat) o[24 + p] = sc;
-            else if (p > seat) o[27 + p - 1] = sc;
-        }
+    for (int p = 0; p < P; p++) {  // features.py:276-282, its i-1 indexing quirk kept
+        const float sc = (float)(e.pr[p] >> 24);
+        if (p < seat) o[24 + p] = sc;
+        else if (p > seat) o[27 + p - 1] = sc;
     }
 }
 

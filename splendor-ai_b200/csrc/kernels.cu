@@ -3,12 +3,12 @@
 //   playout_kernel      thread-per-game, state in registers for the whole game: reset -> {terminal test, legal count,
 //                       Philox choice, k-th legal action, apply} x steps -> calScore -> counters.  No HBM traffic inside
 //                       the loop except the optional trace.
-//   legal_mask_kernel   warp-per-env: lanes own board slots / colours / colour combinations / cards, set bits of the
-//                       3510-bit mask in shared memory, and the warp writes the 110 words coalesced.
+//   legal_mask_kernel   thread-per-env rule work into a shared-memory tile (one 3510-bit row per thread, built from 32/64-bit
+//                       group patterns), then the block streams the tile to HBM coalesced.
 //   step_kernel         thread-per-env: decode the ALL_ACTIONS index, membership test, apply, reward / done / illegal.
-//   observe_kernel      warp-per-env: 265-float observation assembled in shared memory, coalesced store.
-//   env_step_kernel     thread-per-env learner move + in-kernel random opponents, then warp-per-env mask + observation
-//                       out of shared memory (the PPO rollout call).
+//   observe_kernel      same tile scheme for the 265-float observation.
+//   env_step_kernel     the PPO rollout call: learner move + in-kernel random opponents + the learner's next mask and
+//                       observation, one thread per env, state read and written once.
 //   reset / inject / final_scores: thread-per-env.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -233,79 +233,100 @@ __global__ void __launch_bounds__(BLOCK) final_scores_kernel(const uint4 *state,
     if (end_kind) end_kind[i] = (uint8_t)game_ends(e, flags);
 }
 
-// ---------------------------------------------------------------------------------------------- legal mask (warp per env)
-template <int P>
-__global__ void __launch_bounds__(BLOCK) legal_mask_kernel(const uint4 *state, uint32_t *mask, int64_t N)
+// ---------------------------------------------------------------------------------------------- tiles
+// mask / observation kernels: one thread computes one env's row into a shared-memory tile (engine.cuh thread_fill_*),
+// then the block streams the tile to HBM with fully coalesced 32-bit stores (rows are contiguous in the output).
+extern __shared__ __align__(16) uint32_t dyn_tile[];
+
+template <int TB>
+__device__ __forceinline__ void tile_zero(uint32_t *tile, int words)
 {
-    __shared__ Tables sT;
-    __shared__ uint32_t sm[BLOCK / 32][MASK_PAD];
-    stage_tables(sT);
+    uint4 *t4 = reinterpret_cast<uint4 *>(tile);
+    for (int i = threadIdx.x; i < words / 4; i += TB) t4[i] = make_uint4(0, 0, 0, 0);
+    for (int i = (words & ~3) + threadIdx.x; i < words; i += TB) tile[i] = 0;
+}
+// rows [0, n) of `row_words` used words (row stride `row_stride` in the tile) -> out[0 .. n*row_words)
+template <int TB>
+__device__ __forceinline__ void tile_store(const uint32_t *tile, uint32_t *out, int n, int row_words, int row_stride)
+{
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
-    uint32_t *m = sm[warp];
-    for (int64_t i = (int64_t)blockIdx.x * (BLOCK / 32) + warp; i < N; i += nwarps) {
-        for (int w = lane; w < MASK_PAD; w += 32) m[w] = 0;
-        Env<P> e;
-        load_env(e, state, N, i);  // same address in every lane: one broadcast transaction per chunk
-        Ctx c;
-        make_ctx(e, sT, c);
-        __syncwarp();
-        const bool any = lane_fill_mask(e, sT, c, m, lane);
-        if (__ballot_sync(0xFFFFFFFFu, any) == 0 && lane == 0) set_for_nobles(m, 0, 1, c.S);  // pass (:570-574)
-        __syncwarp();
-        uint32_t *out = mask + i * SPL_MASK_WORDS;
-        for (int w = lane; w < SPL_MASK_WORDS; w += 32) out[w] = m[w];
-        __syncwarp();
+    for (int j = warp; j < n; j += TB / 32) {
+        const uint32_t *src = tile + j * row_stride;
+        uint32_t *dst = out + (int64_t)j * row_words;
+        for (int w = lane; w < row_words; w += 32) dst[w] = src[w];
     }
 }
 
-// ---------------------------------------------------------------------------------------------- observation (warp per env)
+constexpr int MASK_TB = 64;
+constexpr int OBS_TB = 64;
+constexpr int ENVSTEP_TB = 64;
+
 template <int P>
-__global__ void __launch_bounds__(BLOCK) observe_kernel(const uint4 *state, const int8_t *seat, float *obs, int64_t N)
+__global__ void __launch_bounds__(MASK_TB) legal_mask_kernel(const uint4 *state, uint32_t *mask, int64_t N)
 {
     __shared__ Tables sT;
-    __shared__ float so[BLOCK / 32][OBS_PAD];
-    __shared__ uint32_t sscr[BLOCK / 32][16];
+    uint32_t *tile = dyn_tile;  // MASK_TB x MASK_ROW words
     stage_tables(sT);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
-    for (int64_t i = (int64_t)blockIdx.x * (BLOCK / 32) + warp; i < N; i += nwarps) {
-        Env<P> e;
-        load_env(e, state, N, i);
-        const int s = seat ? (int)seat[i] : seat_of(e.meta);
-        for (int w = lane; w < OBS_PAD; w += 32) so[warp][w] = 0.f;
-        __syncwarp();
-        lane_fill_obs_cards(e, sT, s, so[warp], sscr[warp], lane);
-        __syncwarp();
-        lane_fill_obs_rest(e, sT, g_log1p_bits, s, so[warp], sscr[warp], lane);
-        __syncwarp();
-        float *out = obs + i * SPL_OBS_SIZE;
-        for (int w = lane; w < SPL_OBS_SIZE; w += 32) out[w] = so[warp][w];
-        __syncwarp();
+    for (int64_t base = (int64_t)blockIdx.x * MASK_TB; base < N; base += (int64_t)gridDim.x * MASK_TB) {
+        tile_zero<MASK_TB>(tile, MASK_TB * MASK_ROW);
+        __syncthreads();
+        const int64_t i = base + threadIdx.x;
+        if (i < N) {
+            Env<P> e;
+            load_env(e, state, N, i);
+            Ctx c;
+            make_ctx(e, sT, c);
+            thread_fill_mask(e, sT, c, tile + threadIdx.x * MASK_ROW);
+        }
+        __syncthreads();
+        tile_store<MASK_TB>(tile, mask + base * SPL_MASK_WORDS, (int)min((int64_t)MASK_TB, N - base), SPL_MASK_WORDS, MASK_ROW);
+        __syncthreads();
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(OBS_TB) observe_kernel(const uint4 *state, const int8_t *seat, float *obs, int64_t N)
+{
+    __shared__ Tables sT;
+    uint32_t *tile = dyn_tile;  // OBS_TB x OBS_ROW floats
+    stage_tables(sT);
+    for (int64_t base = (int64_t)blockIdx.x * OBS_TB; base < N; base += (int64_t)gridDim.x * OBS_TB) {
+        tile_zero<OBS_TB>(tile, OBS_TB * OBS_ROW);
+        __syncthreads();
+        const int64_t i = base + threadIdx.x;
+        if (i < N) {
+            Env<P> e;
+            load_env(e, state, N, i);
+            thread_fill_obs(e, sT, g_log1p_bits, seat ? (int)seat[i] : seat_of(e.meta), reinterpret_cast<float *>(tile) + threadIdx.x * OBS_ROW);
+        }
+        __syncthreads();
+        tile_store<OBS_TB>(tile, reinterpret_cast<uint32_t *>(obs) + base * SPL_OBS_SIZE, (int)min((int64_t)OBS_TB, N - base), SPL_OBS_SIZE, OBS_ROW);
+        __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------------------------- PPO env step
-// Phase 1 (thread per env): the learner's action, then RandomAgent opponents until the learner's seat or the end.
-// Phase 2 (warp per env, state handed over through shared memory): the learner's next mask and observation.
+// One thread per env, everything out of registers: the learner's action (membership-checked), RandomAgent opponents until
+// the learner's seat or the end (_simulate_opponents, splendor_env.py:219-231), then the learner's next legal mask and
+// observation built into the block's tile and stored coalesced.  The state is read and written exactly once.
 template <int P>
-__global__ void __launch_bounds__(BLOCK) env_step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
-                                                         const uint64_t *game_ids, const int8_t *learner, const int16_t *action, int8_t *reward,
-                                                         uint8_t *terminated, uint8_t *illegal, uint32_t *mask, float *obs,
-                                                         int64_t N, uint32_t flags)
+__global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+                                                              const uint64_t *game_ids, const int8_t *learner, const int16_t *action,
+                                                              int8_t *reward, uint8_t *terminated, uint8_t *illegal, uint32_t *mask,
+                                                              float *obs, int64_t N, uint32_t flags)
 {
     __shared__ Tables sT;
-    __shared__ uint4 sst[2 + P][BLOCK];
-    __shared__ uint32_t sm[BLOCK / 32][MASK_PAD];
-    __shared__ float so[BLOCK / 32][OBS_PAD];
-    __shared__ uint32_t sscr[BLOCK / 32][16];
-    __shared__ int8_t sseat[BLOCK];
+    uint32_t *tile = dyn_tile;  // ENVSTEP_TB x OBS_ROW words, used for the mask rows first and the observation rows second
     stage_tables(sT);
-    const int64_t base = (int64_t)blockIdx.x * BLOCK, i = base + threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * ENVSTEP_TB, i = base + threadIdx.x;
+    const int n_rows = (int)min((int64_t)ENVSTEP_TB, N - base);
+    Env<P> e;
+    int me = 0;
+    if (mask) tile_zero<ENVSTEP_TB>(tile, ENVSTEP_TB * MASK_ROW);
     if (i < N) {
-        Env<P> e;
         load_env(e, state, N, i);
-        const int me = learner[i], a = action[i];
+        me = learner[i];
+        const int a = action[i];
         const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
         int rew = 0, bad = 0;
         bool go = true;
@@ -317,15 +338,14 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(uint4 *state, const uin
                 rew = apply_action(e, ch, src);
             else { bad = 1; go = false; e.meta |= META_ILLEGAL; }
         }
-        // _simulate_opponents (splendor_env.py:219-231)
         for (int guard = 0; go && guard < 4; guard++) {
             if (seat_of(e.meta) == me || game_ends(e, flags) != SPL_END_NONE) break;
             Ctx c;
             FamilyCounts f;
             Choice ch;
+            const uint32_t r = philox(seed, src.game, turns_total(e), STREAM_ACTION).x;
             make_ctx(e, sT, c);
             const int total = count_legal(e, sT, c, f);
-            const uint32_t r = philox(seed, src.game, turns_total(e), STREAM_ACTION).x;
             select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
             apply_action(e, ch, src);
         }
@@ -333,44 +353,26 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(uint4 *state, const uin
         if (reward) reward[i] = (int8_t)rew;
         if (illegal) illegal[i] = (uint8_t)bad;
         if (terminated) terminated[i] = (uint8_t)game_ends(e, flags);
-        sst[0][threadIdx.x] = make_uint4(e.bank, e.d[0], e.d[1], e.d[2]);
-        sst[1][threadIdx.x] = make_uint4(e.k[0], e.k[1], e.k[2], e.meta);
-#pragma unroll
-        for (int p = 0; p < P; p++) sst[2 + p][threadIdx.x] = make_uint4(e.pg[p], e.pc[p], e.pr[p], e.pi[p]);
-        sseat[threadIdx.x] = (int8_t)me;
     }
-    __syncthreads();
-    if (!mask && !obs) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int j = warp; j < BLOCK && base + j < N; j += BLOCK / 32) {
-        Env<P> e;
-        load_env(e, &sst[0][0], BLOCK, j);
-        const int me = sseat[j];
-        // the mask/observation are the LEARNER's (get_legal_actions_mask / _vectorize use my_turn, splendor_env.py:184,206)
-        Env<P> el = e;
-        el.meta = (e.meta & ~(3u << 20)) | ((uint32_t)me << 20);
-        if (mask) {
-            for (int w = lane; w < MASK_PAD; w += 32) sm[warp][w] = 0;
+    if (mask) {  // the LEARNER's mask (get_legal_actions_mask uses my_turn, splendor_env.py:184)
+        __syncthreads();
+        if (i < N) {
+            Env<P> el = e;
+            el.meta = (e.meta & ~(3u << 20)) | ((uint32_t)me << 20);
             Ctx c;
             make_ctx(el, sT, c);
-            __syncwarp();
-            const bool any = lane_fill_mask(el, sT, c, sm[warp], lane);
-            if (__ballot_sync(0xFFFFFFFFu, any) == 0 && lane == 0) set_for_nobles(sm[warp], 0, 1, c.S);
-            __syncwarp();
-            uint32_t *out = mask + (base + j) * SPL_MASK_WORDS;
-            for (int w = lane; w < SPL_MASK_WORDS; w += 32) out[w] = sm[warp][w];
+            thread_fill_mask(el, sT, c, tile + threadIdx.x * MASK_ROW);
         }
-        if (obs) {
-            for (int w = lane; w < OBS_PAD; w += 32) so[warp][w] = 0.f;
-            __syncwarp();
-            lane_fill_obs_cards(e, sT, me, so[warp], sscr[warp], lane);
-            __syncwarp();
-            lane_fill_obs_rest(e, sT, g_log1p_bits, me, so[warp], sscr[warp], lane);
-            __syncwarp();
-            float *out = obs + (base + j) * SPL_OBS_SIZE;
-            for (int w = lane; w < SPL_OBS_SIZE; w += 32) out[w] = so[warp][w];
-        }
-        __syncwarp();
+        __syncthreads();
+        tile_store<ENVSTEP_TB>(tile, mask + base * SPL_MASK_WORDS, n_rows, SPL_MASK_WORDS, MASK_ROW);
+    }
+    if (obs) {
+        __syncthreads();
+        tile_zero<ENVSTEP_TB>(tile, ENVSTEP_TB * OBS_ROW);
+        __syncthreads();
+        if (i < N) thread_fill_obs(e, sT, g_log1p_bits, me, reinterpret_cast<float *>(tile) + threadIdx.x * OBS_ROW);
+        __syncthreads();
+        tile_store<ENVSTEP_TB>(tile, reinterpret_cast<uint32_t *>(obs) + base * SPL_OBS_SIZE, n_rows, SPL_OBS_SIZE, OBS_ROW);
     }
 }
 
@@ -406,6 +408,25 @@ static int sm_count()
         if (sms <= 0) sms = 148;
     }
     return sms;
+}
+
+// kernels whose tile exceeds the 48 KB default opt in to large dynamic shared memory once per device
+static int allow_big_smem()
+{
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || done[dev]) return SPL_OK;
+    constexpr int bytes = OBS_TB * OBS_ROW * 4;
+    static_assert(ENVSTEP_TB == OBS_TB, "one attribute value covers both kernels");
+    CK(cudaFuncSetAttribute(observe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(observe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(observe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(env_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(env_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(env_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done[dev] = true;
+    return SPL_OK;
 }
 
 #define DISPATCH_P(P, ...)             \
@@ -468,9 +489,10 @@ int spl_legal_mask(const void *state, uint32_t *mask, int64_t N, int P, void *st
     if (!state || !mask || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    const int64_t want = (N + BLOCK / 32 - 1) / (BLOCK / 32), cap = (int64_t)sm_count() * 16;
+    constexpr size_t smem = (size_t)MASK_TB * MASK_ROW * 4;
+    const int64_t want = (N + MASK_TB - 1) / MASK_TB, cap = (int64_t)sm_count() * 6;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    DISPATCH_P(P, legal_mask_kernel<PP><<<grid, BLOCK, 0, (cudaStream_t)stream>>>((const uint4 *)state, mask, N));
+    DISPATCH_P(P, legal_mask_kernel<PP><<<grid, MASK_TB, smem, (cudaStream_t)stream>>>((const uint4 *)state, mask, N));
     CK(cudaGetLastError());
     return SPL_OK;
 }
@@ -504,9 +526,11 @@ int spl_observe(const void *state, const int8_t *seat, float *obs, int64_t N, in
     if (!state || !obs || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    const int64_t want = (N + BLOCK / 32 - 1) / (BLOCK / 32), cap = (int64_t)sm_count() * 16;
+    constexpr size_t smem = (size_t)OBS_TB * OBS_ROW * 4;
+    if (int rc = allow_big_smem()) return rc;
+    const int64_t want = (N + OBS_TB - 1) / OBS_TB, cap = (int64_t)sm_count() * 3;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    DISPATCH_P(P, observe_kernel<PP><<<grid, BLOCK, 0, (cudaStream_t)stream>>>((const uint4 *)state, seat, obs, N));
+    DISPATCH_P(P, observe_kernel<PP><<<grid, OBS_TB, smem, (cudaStream_t)stream>>>((const uint4 *)state, seat, obs, N));
     CK(cudaGetLastError());
     return SPL_OK;
 }
@@ -555,7 +579,9 @@ int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t firs
     if (!state || !learner || !action || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    DISPATCH_P(P, env_step_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
+    constexpr size_t smem = (size_t)ENVSTEP_TB * OBS_ROW * 4;
+    if (int rc = allow_big_smem()) return rc;
+    DISPATCH_P(P, env_step_kernel<PP><<<grid_for(N, ENVSTEP_TB), ENVSTEP_TB, smem, (cudaStream_t)stream>>>(
                       (uint4 *)state, decks, seed, first_game, game_ids, learner, action, reward, terminated, illegal, mask, obs, N, flags));
     CK(cudaGetLastError());
     return SPL_OK;

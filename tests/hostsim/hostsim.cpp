@@ -102,10 +102,8 @@ template <int P> static int t_mask(const uint32_t *w, int seat, uint32_t *mask)
     Env<P> e; ld(e, w);
     if (seat >= 0) e.meta = (e.meta & ~(3u << 20)) | ((uint32_t)seat << 20);
     Ctx c; make_ctx(e, T, c);
-    uint32_t m[MASK_PAD] = {0};
-    bool any = false;
-    for (int lane = 0; lane < 32; lane++) any |= lane_fill_mask(e, T, c, m, lane);
-    if (!any) set_for_nobles(m, 0, 1, c.S);
+    uint32_t m[MASK_ROW] = {0};
+    thread_fill_mask(e, T, c, m);
     std::memcpy(mask, m, SPL_MASK_WORDS * 4);
     return 0;
 }
@@ -126,10 +124,8 @@ template <int P> static int t_step(uint32_t *w, const uint8_t *lists, uint64_t s
 template <int P> static int t_observe(const uint32_t *w, int seat, float *o)
 {
     Env<P> e; ld(e, w);
-    float buf[OBS_PAD] = {0};
-    uint32_t scratch[16] = {0};
-    for (int lane = 0; lane < 32; lane++) lane_fill_obs_cards(e, T, seat, buf, scratch, lane);
-    for (int lane = 0; lane < 32; lane++) lane_fill_obs_rest(e, T, LOG1P, seat, buf, scratch, lane);
+    float buf[OBS_ROW] = {0};
+    thread_fill_obs(e, T, LOG1P, seat, buf);
     std::memcpy(o, buf, SPL_OBS_SIZE * 4);
     return 0;
 }

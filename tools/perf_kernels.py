@@ -1,0 +1,72 @@
+"""Time the single-call kernels (legal mask, step, observe, fused PPO env-step) on mid-game states and report achieved
+HBM GB/s against algorithmic bytes.  Usage: python tools/perf_kernels.py [--envs 262144] [--players 2] [--reps 20]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import splendor_ai_b200 as pkg
+from splendor_ai_b200.env import unpack_mask
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--envs", type=int, nargs="+", default=[262144])
+ap.add_argument("--players", type=int, default=2)
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--advance", type=int, default=30, help="env-steps played before timing (mid-game states)")
+a = ap.parse_args()
+PEAK = 6533.8
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+for N in a.envs:
+    P = a.players
+    W = (8 + 4 * P) * 4
+    eng = pkg.BatchedSplendor(N, P, seed=1234, limit_rounds=True)
+    gen = torch.Generator(device=eng.device).manual_seed(0)
+    learner = torch.zeros(N, dtype=torch.int8, device=eng.device)
+    skip = torch.full((N,), -1, dtype=torch.int16, device=eng.device)
+    obs, rew, term, ill, mask = eng.env_step(learner, skip)
+
+    def sample(mask):
+        return torch.multinomial(unpack_mask(mask, torch.float32), 1, generator=gen).squeeze(1).to(torch.int16)
+
+    for _ in range(a.advance // 2):
+        obs, rew, term, ill, mask = eng.env_step(learner, sample(mask))
+    saved = eng.state.clone()
+    act = sample(mask)
+    mask_buf = torch.empty((N, 110), dtype=torch.int32, device=eng.device)
+    obs_buf = torch.empty((N, 265), dtype=torch.float32, device=eng.device)
+    res = {}
+    res["legal_mask"] = (timed(lambda: eng.legal_mask(out=mask_buf), a.reps), W + 440)
+    res["observe"] = (timed(lambda: eng.observe(out=obs_buf), a.reps), W + 1060)
+
+    def do_step():
+        eng.state.copy_(saved)
+        eng.step(act)
+
+    def do_env_step():
+        eng.state.copy_(saved)
+        eng.env_step(learner, act)
+
+    copy_ms = timed(lambda: eng.state.copy_(saved), a.reps)
+    res["step"] = (timed(do_step, a.reps) - copy_ms, 2 * W + 2 + 3)
+    res["env_step"] = (timed(do_env_step, a.reps) - copy_ms, 2 * W + 440 + 1060 + 3 + 3)
+    for k, (ms, bytes_per_env) in res.items():
+        gbs = N * bytes_per_env / (ms * 1e-3) / 1e9
+        print(json.dumps({"kernel": k, "envs": N, "players": P, "ms": ms, "envs_per_s": N / (ms * 1e-3), "bytes_per_env": bytes_per_env,
+                          "GBps": gbs, "frac_of_hbm_peak": gbs / PEAK}))
