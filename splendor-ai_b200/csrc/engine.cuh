@@ -776,7 +776,11 @@ __device__ __forceinline__ void final_scores(const Env<P> &e, int (&score2)[P], 
 // env; it spent ~500-800 warp-instructions per env with most lanes idle and reached only 6-7 % of HBM bandwidth
 // (profiles/r1_kernels.md), so the rule work moved to one thread and only the data movement stays cooperative.
 constexpr int MASK_ROW = 113;  // words per thread row: 110 used, odd stride (bank spread), 3 spare for or_bits' overhang
-constexpr int OBS_ROW = 265;   // floats per thread row (265 is odd: conflict-free across lanes as is)
+constexpr int OBS_ROW_BYTES = 276;  // observation staged as BYTES: 265 entries + 4 spill bytes, 69-word (odd) row stride
+// Every observation entry is an integer in 0..255 except three, which thread_fill_obs stashes and obs_entry decodes:
+//   [1]  turns            16 bits in row[267..268]
+//   [6]  np.var numerator 16 bits in row[265..266] (5*sum(x^2) - sum(x)^2 <= 4900), divided by 25 on the way out
+//   [19..23] log(1+bp)    the table index bp in the byte, looked up on the way out
 
 // OR a bit pattern into the row at an arbitrary bit offset (row zeroed beforehand; plain read-modify-write: the row is
 // private to the thread)
@@ -900,9 +904,21 @@ __device__ __forceinline__ uint32_t insert_sorted4(uint32_t t, uint32_t d)
     return t0 | t1 << 8 | t2 << 16 | min(a3, r2) << 24;
 }
 
-// features.extract_metrics_with_cards(state, seat).astype(float32) (features.py:214-310, :377-480) into the zeroed row o
+// float32 value of observation entry w from a staged byte row
+__device__ __forceinline__ float obs_entry(const uint8_t *row, int w, const uint32_t *log1p_bits)
+{
+    const uint32_t b = row[w];
+    float f = (float)b;
+    if (w == 1) f = (float)(row[267] | row[268] << 8);
+    // np.var of five small integers = (5*sum(x^2) - sum(x)^2) / 25; numerator < 2^24, IEEE division: exact rounding
+    if (w == 6) f = __fdiv_rn((float)(row[265] | row[266] << 8), 25.0f);
+    if (w >= 19 && w < 24) f = __uint_as_float(log1p_bits[b & 31u]);
+    return f;
+}
+
+// features.extract_metrics_with_cards(state, seat).astype(float32) (features.py:214-310, :377-480) into the zeroed byte row o
 template <int P>
-__device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T, const uint32_t *log1p_bits, int seat, float *o)
+__device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T, int seat, uint8_t *o)
 {
     uint32_t gems = e.pg[0], cards = e.pc[0], resv = e.pr[0], pinfo = e.pi[0];
 #pragma unroll
@@ -923,23 +939,23 @@ __device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T
 #pragma unroll
         for (int f = 0; f < 6; f++) mx = max(mx, field(miss, 5 * f));
         const uint32_t turns = sum == 0 ? 0u : max((sum + 2u) / 3u, mx);  // features.py:124-135
-        o[(s < 12 ? 30 : 54 - 12) + s] = (float)sum;
-        o[(s < 12 ? 42 : 57 - 12) + s] = (float)turns;
+        o[(s < 12 ? 30 : 54 - 12) + s] = (uint8_t)sum;
+        o[(s < 12 ? 42 : 57 - 12) + s] = (uint8_t)turns;
 #pragma unroll
         for (int f = 0; f < 6; f++)
             if (f != 2 && sh == 5u * f) best[f] = insert_sorted4(best[f], sum);
         // vectorize_card (features.py:377-413): one-hot over sklearn's alphabetical categories black, blue, green, red,
         // white, yellow; the cost in alphabetical order black, blue, green, red, white; deck_id; points
-        float *v = o + 70 + 13 * s;
+        uint8_t *v = o + 70 + 13 * s;
         const int fld = (int)(sh / 5u);  // 0 black 1 red 3 green 4 blue 5 white
-        v[fld == 0 ? 0 : (fld == 1 ? 3 : (fld == 3 ? 2 : (fld == 4 ? 1 : 4)))] = 1.f;
-        v[6] = (float)field(cw.x, 0);
-        v[7] = (float)field(cw.x, 20);
-        v[8] = (float)field(cw.x, 15);
-        v[9] = (float)field(cw.x, 5);
-        v[10] = (float)field(cw.x, 25);
-        v[11] = (float)(cw.y >> 8 & 3u);
-        v[12] = (float)(cw.y >> 5 & 7u);
+        v[fld == 0 ? 0 : (fld == 1 ? 3 : (fld == 3 ? 2 : (fld == 4 ? 1 : 4)))] = 1;
+        v[6] = (uint8_t)field(cw.x, 0);
+        v[7] = (uint8_t)field(cw.x, 20);
+        v[8] = (uint8_t)field(cw.x, 15);
+        v[9] = (uint8_t)field(cw.x, 5);
+        v[10] = (uint8_t)field(cw.x, 25);
+        v[11] = (uint8_t)(cw.y >> 8 & 3u);
+        v[12] = (uint8_t)(cw.y >> 5 & 7u);
     }
     // distance to each board noble (features.py:257-274)
 #pragma unroll 1
@@ -955,34 +971,34 @@ __device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T
             dist += (cnt >= 1 ? t & 0xFFu : 0u) + (cnt >= 2 ? (t >> 8) & 0xFFu : 0u) + (cnt >= 3 ? (t >> 16) & 0xFFu : 0u) +
                     (cnt >= 4 ? t >> 24 : 0u);
         }
-        o[60 + k] = (float)dist;
-        o[65 + k] = (float)hsum6_small(missing);
+        o[60 + k] = (uint8_t)dist;
+        o[65 + k] = (uint8_t)hsum6_small(missing);
     }
     // the scalar metrics (features.py:284-299)
     const uint32_t score = resv >> 24;
-    o[0] = 1.f;
-    o[1] = (float)(pinfo & 0xFFFFu);
-    o[2] = (float)score;
-    o[3] = score >= 15u ? 1.f : 0.f;
-    o[4] = (float)hsum6(cards);
-    o[5] = (float)__popc(~resv & 0x00808080u);
+    o[0] = 1;
+    o[267] = (uint8_t)pinfo; o[268] = (uint8_t)(pinfo >> 8);
+    o[2] = (uint8_t)score;
+    o[3] = score >= 15u ? 1 : 0;
+    o[4] = (uint8_t)hsum6(cards);
+    o[5] = (uint8_t)__popc(~resv & 0x00808080u);
     int s1 = 0, s2 = 0;
 #pragma unroll
     for (int n = 0; n < 5; n++) {
         const int sh = 5 * field_of_normal(n);
         const int b = (int)field(bp, sh);
         s1 += b; s2 += b * b;
-        o[9 + n] = (float)field(cards, sh);
-        o[14 + n] = (float)b;
-        o[19 + n] = __uint_as_float(log1p_bits[b]);
+        o[9 + n] = (uint8_t)field(cards, sh);
+        o[14 + n] = (uint8_t)b;
+        o[19 + n] = (uint8_t)b;
     }
-    // np.var of five small integers = (5*sum(x^2) - sum(x)^2) / 25; numerator < 2^24, IEEE division: exact rounding
-    o[6] = __fdiv_rn((float)(5 * s2 - s1 * s1), 25.0f);
-    o[7] = (float)field(gems, YSH);
-    o[8] = (float)hsum6(gems);
+    const int var_num = 5 * s2 - s1 * s1;
+    o[265] = (uint8_t)var_num; o[266] = (uint8_t)(var_num >> 8);
+    o[7] = (uint8_t)field(gems, YSH);
+    o[8] = (uint8_t)hsum6(gems);
 #pragma unroll
     for (int p = 0; p < P; p++) {  // features.py:276-282, its i-1 indexing quirk kept
-        const float sc = (float)(e.pr[p] >> 24);
+        const uint8_t sc = (uint8_t)(e.pr[p] >> 24);
         if (p < seat) o[24 + p] = sc;
         else if (p > seat) o[27 + p - 1] = sc;
     }

@@ -245,6 +245,17 @@ __device__ __forceinline__ void tile_zero(uint32_t *tile, int words)
     for (int i = threadIdx.x; i < words / 4; i += TB) t4[i] = make_uint4(0, 0, 0, 0);
     for (int i = (words & ~3) + threadIdx.x; i < words; i += TB) tile[i] = 0;
 }
+// staged byte rows -> float32 observations, coalesced
+template <int TB>
+__device__ __forceinline__ void tile_store_obs(const uint8_t *tile, float *out, int n, int row_stride_bytes)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < n; j += TB / 32) {
+        const uint8_t *row = tile + j * row_stride_bytes;
+        float *dst = out + (int64_t)j * SPL_OBS_SIZE;
+        for (int w = lane; w < SPL_OBS_SIZE; w += 32) dst[w] = obs_entry(row, w, g_log1p_bits);
+    }
+}
 // rows [0, n) of `row_words` used words (row stride `row_stride` in the tile) -> out[0 .. n*row_words)
 template <int TB>
 __device__ __forceinline__ void tile_store(const uint32_t *tile, uint32_t *out, int n, int row_words, int row_stride)
@@ -258,8 +269,9 @@ __device__ __forceinline__ void tile_store(const uint32_t *tile, uint32_t *out, 
 }
 
 constexpr int MASK_TB = 64;
-constexpr int OBS_TB = 64;
+constexpr int OBS_TB = 128;
 constexpr int ENVSTEP_TB = 64;
+constexpr int ENVSTEP_ROW_BYTES = MASK_ROW * 4 > OBS_ROW_BYTES ? MASK_ROW * 4 : OBS_ROW_BYTES;
 
 template <int P>
 __global__ void __launch_bounds__(MASK_TB) legal_mask_kernel(const uint4 *state, uint32_t *mask, int64_t N)
@@ -288,19 +300,19 @@ template <int P>
 __global__ void __launch_bounds__(OBS_TB) observe_kernel(const uint4 *state, const int8_t *seat, float *obs, int64_t N)
 {
     __shared__ Tables sT;
-    uint32_t *tile = dyn_tile;  // OBS_TB x OBS_ROW floats
+    uint32_t *tile = dyn_tile;  // OBS_TB byte rows of OBS_ROW_BYTES
     stage_tables(sT);
     for (int64_t base = (int64_t)blockIdx.x * OBS_TB; base < N; base += (int64_t)gridDim.x * OBS_TB) {
-        tile_zero<OBS_TB>(tile, OBS_TB * OBS_ROW);
+        tile_zero<OBS_TB>(tile, OBS_TB * OBS_ROW_BYTES / 4);
         __syncthreads();
         const int64_t i = base + threadIdx.x;
         if (i < N) {
             Env<P> e;
             load_env(e, state, N, i);
-            thread_fill_obs(e, sT, g_log1p_bits, seat ? (int)seat[i] : seat_of(e.meta), reinterpret_cast<float *>(tile) + threadIdx.x * OBS_ROW);
+            thread_fill_obs(e, sT, seat ? (int)seat[i] : seat_of(e.meta), reinterpret_cast<uint8_t *>(tile) + threadIdx.x * OBS_ROW_BYTES);
         }
         __syncthreads();
-        tile_store<OBS_TB>(tile, reinterpret_cast<uint32_t *>(obs) + base * SPL_OBS_SIZE, (int)min((int64_t)OBS_TB, N - base), SPL_OBS_SIZE, OBS_ROW);
+        tile_store_obs<OBS_TB>(reinterpret_cast<const uint8_t *>(tile), obs + base * SPL_OBS_SIZE, (int)min((int64_t)OBS_TB, N - base), OBS_ROW_BYTES);
         __syncthreads();
     }
 }
@@ -316,7 +328,7 @@ __global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, cons
                                                               float *obs, int64_t N, uint32_t flags)
 {
     __shared__ Tables sT;
-    uint32_t *tile = dyn_tile;  // ENVSTEP_TB x OBS_ROW words, used for the mask rows first and the observation rows second
+    uint32_t *tile = dyn_tile;  // ENVSTEP_TB rows of ENVSTEP_ROW_BYTES: the mask rows first, then the observation byte rows
     stage_tables(sT);
     const int64_t base = (int64_t)blockIdx.x * ENVSTEP_TB, i = base + threadIdx.x;
     const int n_rows = (int)min((int64_t)ENVSTEP_TB, N - base);
@@ -368,11 +380,11 @@ __global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, cons
     }
     if (obs) {
         __syncthreads();
-        tile_zero<ENVSTEP_TB>(tile, ENVSTEP_TB * OBS_ROW);
+        tile_zero<ENVSTEP_TB>(tile, ENVSTEP_TB * OBS_ROW_BYTES / 4);
         __syncthreads();
-        if (i < N) thread_fill_obs(e, sT, g_log1p_bits, me, reinterpret_cast<float *>(tile) + threadIdx.x * OBS_ROW);
+        if (i < N) thread_fill_obs(e, sT, me, reinterpret_cast<uint8_t *>(tile) + threadIdx.x * OBS_ROW_BYTES);
         __syncthreads();
-        tile_store<ENVSTEP_TB>(tile, reinterpret_cast<uint32_t *>(obs) + base * SPL_OBS_SIZE, n_rows, SPL_OBS_SIZE, OBS_ROW);
+        tile_store_obs<ENVSTEP_TB>(reinterpret_cast<const uint8_t *>(tile), obs + base * SPL_OBS_SIZE, n_rows, OBS_ROW_BYTES);
     }
 }
 
@@ -408,25 +420,6 @@ static int sm_count()
         if (sms <= 0) sms = 148;
     }
     return sms;
-}
-
-// kernels whose tile exceeds the 48 KB default opt in to large dynamic shared memory once per device
-static int allow_big_smem()
-{
-    static bool done[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || done[dev]) return SPL_OK;
-    constexpr int bytes = OBS_TB * OBS_ROW * 4;
-    static_assert(ENVSTEP_TB == OBS_TB, "one attribute value covers both kernels");
-    CK(cudaFuncSetAttribute(observe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(observe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(observe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(env_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(env_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(env_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    done[dev] = true;
-    return SPL_OK;
 }
 
 #define DISPATCH_P(P, ...)             \
@@ -526,9 +519,8 @@ int spl_observe(const void *state, const int8_t *seat, float *obs, int64_t N, in
     if (!state || !obs || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    constexpr size_t smem = (size_t)OBS_TB * OBS_ROW * 4;
-    if (int rc = allow_big_smem()) return rc;
-    const int64_t want = (N + OBS_TB - 1) / OBS_TB, cap = (int64_t)sm_count() * 3;
+    constexpr size_t smem = (size_t)OBS_TB * OBS_ROW_BYTES;
+    const int64_t want = (N + OBS_TB - 1) / OBS_TB, cap = (int64_t)sm_count() * 6;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     DISPATCH_P(P, observe_kernel<PP><<<grid, OBS_TB, smem, (cudaStream_t)stream>>>((const uint4 *)state, seat, obs, N));
     CK(cudaGetLastError());
@@ -579,8 +571,7 @@ int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t firs
     if (!state || !learner || !action || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    constexpr size_t smem = (size_t)ENVSTEP_TB * OBS_ROW * 4;
-    if (int rc = allow_big_smem()) return rc;
+    constexpr size_t smem = (size_t)ENVSTEP_TB * ENVSTEP_ROW_BYTES;
     DISPATCH_P(P, env_step_kernel<PP><<<grid_for(N, ENVSTEP_TB), ENVSTEP_TB, smem, (cudaStream_t)stream>>>(
                       (uint4 *)state, decks, seed, first_game, game_ids, learner, action, reward, terminated, illegal, mask, obs, N, flags));
     CK(cudaGetLastError());

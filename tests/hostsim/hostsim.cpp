@@ -124,9 +124,9 @@ template <int P> static int t_step(uint32_t *w, const uint8_t *lists, uint64_t s
 template <int P> static int t_observe(const uint32_t *w, int seat, float *o)
 {
     Env<P> e; ld(e, w);
-    float buf[OBS_ROW] = {0};
-    thread_fill_obs(e, T, LOG1P, seat, buf);
-    std::memcpy(o, buf, SPL_OBS_SIZE * 4);
+    uint8_t row[OBS_ROW_BYTES] = {0};
+    thread_fill_obs(e, T, seat, row);
+    for (int w = 0; w < SPL_OBS_SIZE; w++) o[w] = obs_entry(row, w, LOG1P);
     return 0;
 }
 template <int P> static int t_scores(const uint32_t *w, uint32_t flags, int *score2, int *outcome, int *kind)
