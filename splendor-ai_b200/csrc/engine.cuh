@@ -48,6 +48,13 @@ struct Tables {
     uint8_t pad[3];
     uint32_t ret_diff[380];  // returned gems (g6) of variant v: 6 / 15 / 20 variants per combo of length 1 / 2 / 3
     uint32_t ret_same[105];  // [c*21 + v], c = NORMAL_COLORS index
+    // feasibility LUTs: which return variants of a group the agent can pay, from its held-colour masks (no scanning)
+    uint8_t pext_diff[25][64];  // 6-bit colour-field mask -> bits over the combo's OTHER colours, in variant order
+    uint8_t pext_same[5][64];   // same for collect_same colour c (5 other colours)
+    uint16_t pairs5[32];        // held>=1 bits over 5 others -> combinations(others, 2) bits (collect_same variants 1..10)
+    uint16_t cwr2_pair[2][16];  // [k==4][x]: k others held>=1 -> bits of the i<j entries of combinations_with_replacement(k,2)
+    uint16_t cwr2_dbl[2][16];   // [k==4][y]: held>=2 -> bits of the (i,i) entries
+    uint16_t cwr3[512];         // k=3: x | y<<3 | z<<6 (held >=1/>=2/>=3) -> bits of combinations_with_replacement(3,3)
 };
 
 namespace detail {
@@ -133,6 +140,62 @@ __host__ __device__ constexpr Tables make_tables()
                     off += V;
                     base += 6 * V;
                 }
+    }
+    // ---- feasibility LUTs
+    for (int ci2 = 0; ci2 < 25; ci2++)
+        for (int h = 0; h < 64; h++) {
+            int k = 0, out = 0;
+            for (int f = 0; f < 6; f++) {
+                if (T.combo_mask[ci2] >> f & 1) continue;
+                if (h >> f & 1) out |= 1 << k;
+                k++;
+            }
+            T.pext_diff[ci2][h] = (uint8_t)out;
+        }
+    for (int c = 0; c < 5; c++)
+        for (int h = 0; h < 64; h++) {
+            int k = 0, out = 0;
+            for (int f = 0; f < 6; f++) {
+                if (f == field_of_normal(c)) continue;
+                if (h >> f & 1) out |= 1 << k;
+                k++;
+            }
+            T.pext_same[c][h] = (uint8_t)out;
+        }
+    for (int x = 0; x < 32; x++) {
+        int bits = 0, r = 0;
+        for (int i = 0; i < 5; i++)
+            for (int j = i + 1; j < 5; j++, r++)
+                if ((x >> i & 1) && (x >> j & 1)) bits |= 1 << r;
+        T.pairs5[x] = (uint16_t)bits;
+    }
+    for (int kk = 3; kk <= 4; kk++)
+        for (int x = 0; x < 16; x++) {
+            int pb = 0, db = 0, r = 0;
+            for (int i = 0; i < kk; i++)
+                for (int j = i; j < kk; j++, r++) {
+                    if (i == j) { if (x >> i & 1) db |= 1 << r; }
+                    else if ((x >> i & 1) && (x >> j & 1)) pb |= 1 << r;
+                }
+            T.cwr2_pair[kk - 3][x] = (uint16_t)pb;
+            T.cwr2_dbl[kk - 3][x] = (uint16_t)db;
+        }
+    for (int v = 0; v < 512; v++) {
+        const int x = v & 7, y = (v >> 3) & 7, z = v >> 6;
+        int bits = 0, r = 0;
+        for (int i = 0; i < 3; i++)
+            for (int j = i; j < 3; j++)
+                for (int l = j; l < 3; l++, r++) {
+                    int need[3] = {0, 0, 0};
+                    need[i]++; need[j]++; need[l]++;
+                    bool ok = true;
+                    for (int q = 0; q < 3; q++) {
+                        const int have = (z >> q & 1) ? 3 : ((y >> q & 1) ? 2 : ((x >> q & 1) ? 1 : 0));
+                        if (need[q] > have) ok = false;
+                    }
+                    if (ok) bits |= 1 << r;
+                }
+        T.cwr3[v] = (uint16_t)bits;
     }
     return T;
 }
@@ -422,6 +485,24 @@ __device__ __forceinline__ int reserve_variants(const Ctx &c)
 }
 __device__ __forceinline__ int combo_len(int ci) { return ci < 5 ? 1 : (ci < 15 ? 2 : 3); }
 
+// Bitmask (bit v = variant v) of the return variants of collect_diff combination ci that the agent can pay when it must
+// return `ex` gems (<= 0: only "return nothing").  Table lookups only: pext of the held-colour masks onto the combo's
+// other colours, then the combinations_with_replacement patterns (actions.py:188-199).
+__device__ __forceinline__ uint32_t diff_variant_bits(const Tables &T, const Ctx &c, int ci, int L, int ex)
+{
+    const uint32_t x = T.pext_diff[ci][c.h1], y = T.pext_diff[ci][c.h2], z = T.pext_diff[ci][c.h3];
+    const int kk = 6 - L;
+    const uint32_t two = L == 1 ? 0u : (uint32_t)(T.cwr2_pair[L == 2][x & 15u] | T.cwr2_dbl[L == 2][y & 15u]);
+    const uint32_t three = L == 3 ? (uint32_t)T.cwr3[x | y << 3 | z << 6] : 0u;
+    return ex <= 0 ? 1u : (ex == 1 ? x << 1 : (ex == 2 ? two << (1 + kk) : three << 10));
+}
+// Same for collect_same colour `col` (actions.py:145-174): none | pairs 1..10 | one of 11..15 | two of 16..20
+__device__ __forceinline__ uint32_t same_variant_bits(const Tables &T, const Ctx &c, int col, int e2)
+{
+    const uint32_t x = T.pext_same[col][c.h1], y = T.pext_same[col][c.h2];
+    return e2 <= 0 ? 1u : (e2 == 1 ? x << 11 : ((uint32_t)T.pairs5[x] << 1 | y << 16));
+}
+
 // resources_sufficient (:371-394): returns true and the payment if the card is affordable and below the 7-card cap
 __device__ __forceinline__ bool can_buy(const Ctx &c, uint2 cw, uint32_t &pay)
 {
@@ -535,7 +616,8 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
         // collect_same (510 + c*126 + n*21 + v) and collect_diff (combo_base + n*V + v): find the group (colour or colour
         // combination), then the noble slot and the vi-th feasible return variant within a range of its table row
         const uint32_t *row;
-        int base, V, nv = 1, v0 = 0, v1 = 0, vsplit = -1;
+        int base, V, nv = 1;
+        uint32_t vbits;
         if (k < f.same) {
             const int e2 = c.hold - 8;
             int col = 0;
@@ -549,8 +631,7 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
             if (col == 4) nv = n_returns(e2, c, 63u & ~(1u << field_of_normal(4)));
             row = T.ret_same + col * 21;
             base = BASE_SAME + col * 126; V = 21;
-            if (e2 == 1) { v0 = 11; v1 = 16; }
-            if (e2 == 2) { v0 = 1; v1 = 11; vsplit = choose2(__popc(c.h1 & 63u & ~(1u << field_of_normal(col)))); }
+            vbits = same_variant_bits(T, c, col, e2);
             ch.type = T_SAME; ch.slot = col;
             ch.C = 2u << (5 * field_of_normal(col));
         } else {
@@ -568,22 +649,15 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
                 k -= nv * c.nS;
             }
             if (ci == ci_end && ex > 0) nv = n_returns(ex, c, 63u & ~(uint32_t)T.combo_mask[ci]);
-            const int kk = 6 - L, r1 = 1 + kk, r2 = r1 + (kk * (kk + 1) >> 1);
             V = L == 1 ? 6 : (L == 2 ? 15 : 20);
             row = T.ret_diff + T.combo_off[ci];
             base = T.combo_base[ci];
-            if (ex == 1) { v0 = 1; v1 = r1; }
-            if (ex == 2) { v0 = r1; v1 = r2; }
-            if (ex == 3) { v0 = r2; v1 = V; }
+            vbits = diff_variant_bits(T, c, ci, L, ex);
             ch.type = T_DIFF; ch.slot = ci;
             ch.C = T.combo_c[ci];
         }
-        const int ni = small_div(k, nv);
-        int vi = k - ni * nv, v = 0;
-        if (v1 > v0) {
-            if (vsplit >= 0 && vi >= vsplit) { vi -= vsplit; v0 = 16; v1 = 21; }  // collect_same: past the pairs -> "two of one colour"
-            v = nth_feasible(row, v0, v1, vi, c.gems);
-        }
+        const int ni = small_div(k, nv), vi = k - ni * nv;
+        const int v = select_bit(vbits, vi);  // the vi-th payable return variant, ascending
         ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
         ch.R = row[v];
         ch.idx = base + ch.n * V + v;
@@ -836,39 +910,35 @@ __device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &
         for (uint32_t occ = c.occ; occ; occ &= occ - 1) or_bits64(m, BASE_RESERVE + 42 * (__ffs(occ) - 1), pat);
         any = true;
     }
-    // collect_same (:475-496)
+    // collect_same (:475-496) and collect_diff (:437-473): every group computes its pattern unconditionally (zero when
+    // the group is not available) - uniform control flow beats skipping work when 32 different games share a warp
+    const uint32_t np_lo = NP & 7u, np_hi = NP >> 3;
+    uint32_t any_bits = 0;
     {
         const int e2 = c.hold - 8;
-#pragma unroll 1
+#pragma unroll
         for (int col = 0; col < 5; col++) {
-            const int fl = field_of_normal(col);
-            if (!(c.A4 >> fl & 1u)) continue;
-            const uint32_t *row = T.ret_same + col * 21;
-            const uint32_t vs = e2 <= 0 ? 1u : (e2 == 1 ? feasible_bits(row, 11, 16, c.gems)
-                                                        : feasible_bits(row, 1, 11, c.gems) | feasible_bits(row, 16, 21, c.gems));
-            if (!vs) continue;
-            or_bits64(m, BASE_SAME + 126 * col, times_nobles(vs, 21, NP));
-            if (NP >> 3) or_bits64(m, BASE_SAME + 126 * col + 63, times_nobles(vs, 21, NP >> 3));
-            any = true;
+            const uint32_t vs = (c.A4 >> field_of_normal(col) & 1u) ? same_variant_bits(T, c, col, e2) : 0u;
+            or_bits64(m, BASE_SAME + 126 * col, times_nobles(vs, 21, np_lo));
+            or_bits64(m, BASE_SAME + 126 * col + 63, times_nobles(vs, 21, np_hi));
+            any_bits |= vs;
         }
     }
-    // collect_diff (:437-473)
-#pragma unroll 1
+#pragma unroll
     for (int ci = 0; ci < 25; ci++) {
+        const int L = ci < 5 ? 1 : (ci < 15 ? 2 : 3), V = L == 1 ? 6 : (L == 2 ? 15 : 20);
         const uint32_t cm = T.combo_mask[ci];
-        const int L = combo_len(ci);
-        if ((cm & ~c.A1) || L < c.Lmin) continue;
-        const int V = L == 1 ? 6 : (L == 2 ? 15 : 20), ex = c.hold + L - 10, kk = 6 - L;
-        const int r1 = 1 + kk, r2 = r1 + (kk * (kk + 1) >> 1);
-        const uint32_t *row = T.ret_diff + T.combo_off[ci];
-        const uint32_t vd = ex <= 0 ? 1u : (ex == 1 ? feasible_bits(row, 1, r1, c.gems)
-                                                    : (ex == 2 ? feasible_bits(row, r1, r2, c.gems) : feasible_bits(row, r2, V, c.gems)));
-        if (!vd) continue;
-        const int base = T.combo_base[ci];
-        or_bits64(m, base, times_nobles(vd, V, NP));
-        if (NP >> 3) or_bits64(m, base + 3 * V, times_nobles(vd, V, NP >> 3));
-        any = true;
+        const bool valid = !(cm & ~c.A1) && L >= c.Lmin;
+        const uint32_t vd = valid ? diff_variant_bits(T, c, ci, L, c.hold + L - 10) : 0u;
+        const int base = BASE_DIFF + (L == 1 ? 36 * ci : (L == 2 ? 180 + 90 * (ci - 5) : 1080 + 120 * (ci - 15)));
+        if (L == 1) or_bits64(m, base, times_nobles(vd, V, np_lo) | times_nobles(vd, V, np_hi) << 18);
+        else {
+            or_bits64(m, base, times_nobles(vd, V, np_lo));
+            or_bits64(m, base + 3 * V, times_nobles(vd, V, np_hi));
+        }
+        any_bits |= vd;
     }
+    any = any || any_bits;
     // buy (:522-568): 6 noble bits per card; board slots 0-4 / 5-9 / 10-11 and the reserved cards as four 32-bit patterns
     {
         const uint32_t eff = (c.gems & ~(31u << YSH)) + c.cards;
