@@ -106,6 +106,14 @@ int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_ga
              const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal, int64_t N, int P, uint32_t flags,
              void *stream);
 
+/* SplendorGameRule.generatePredecessor(state, action, agent_id) (splendor_model.py:156-220): undo one action per env for
+ * seat[e].  Besides the ALL_ACTIONS index the undo needs what the reference reads from the action dict: card[e] = id of
+ * the card that was bought / reserved (0xFF otherwise), noble[e] = id of the noble that was claimed (0xFF if none),
+ * returned[e*6 .. +6] = returned_gems by colour id (for buys: the payment).  action[e] < 0 skips the env.  The seat to
+ * move becomes seat[e] again (the inverse of spl_step); the reference's list-order quirks are kept. */
+int spl_undo(void *state, const int8_t *seat, const int16_t *action, const uint8_t *card, const uint8_t *noble,
+             const uint8_t *returned, int64_t N, int P, void *stream);
+
 /* gameEnds() per env (SPL_END_*), and calScore per seat as 2*score (+1 = the half-point tie-break), plus the
  * win(2)/tie(1)/loss(0) class of general_game_runner.py:416-430.  Output pointers may be null. */
 int spl_final_scores(const void *state, int8_t *score2 /*[N][P]*/, uint8_t *outcome /*[N][P]*/, uint8_t *end_kind /*[N]*/,

@@ -104,6 +104,8 @@ def lib():
         L.orc_playout.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, sp, i16p, C.POINTER(C.c_int)]
         L.orc_playout.restype = C.c_int
         L.orc_playout_many.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, i8p, i32p, i64p, C.c_int]
+        L.orc_undo.argtypes = [sp, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_undo.restype = C.c_int
         L.orc_describe_action.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), u8p, u8p]
         L.orc_describe_action.restype = C.c_int
         _lib = L
@@ -194,3 +196,8 @@ def describe_action(idx: int):
     if rc:
         raise ValueError(idx)
     return t.value, p.value, n.value, col, ret
+
+
+def undo(s: State, seat: int, idx: int, card: int, noble: int, returned) -> int:
+    r = np.ascontiguousarray(returned, np.uint8)
+    return lib().orc_undo(C.byref(s), seat, int(idx), int(card), int(noble), _ptr(r, C.c_uint8))

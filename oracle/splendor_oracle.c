@@ -738,3 +738,53 @@ int orc_describe_action(int idx, int *type, int *p, int *n, uint8_t *collected, 
     memcpy(returned, A.returned, 6);
     return 0;
 }
+
+/* generatePredecessor (splendor_model.py:156-220): undo ALL_ACTIONS[idx] for `seat`.  card = the card that was bought or
+ * reserved (NONE for other actions), noble = the noble id that was claimed (NONE if none), returned[6] = the action's
+ * returned_gems (for buys: the payment the successor computed).  Quirks kept: the undone noble and an un-bought
+ * reserved card are APPENDED to their lists (:201,:210), the card that had been dealt into the slot goes back on top of
+ * its deck (:180,:196), `passed` is set from the undone action (:219), and the seat to move is not touched (that lives
+ * in the rule object). */
+int orc_undo(orc_state *s, int seat, int idx, int card, int noble, const uint8_t *returned)
+{
+    action_t A;
+    if (decode_action(s, seat, idx, &A)) return -1;
+    orc_player *a = &s->pl[seat];
+    int score = 0;
+    if (A.type == T_SAME || A.type == T_DIFF || A.type == T_RESERVE) {
+        for (int c = 0; c < 6; c++) { s->bank[c] += A.collected[c]; a->gems[c] -= A.collected[c]; }
+        for (int c = 0; c < 6; c++) { a->gems[c] += A.returned[c]; s->bank[c] -= A.returned[c]; }
+        if (A.type == T_RESERVE) {
+            int cur = s->dealt[A.p];
+            if (cur != NONE) { int t = card_tier(cur); s->deck[t][s->deck_n[t]++] = (uint8_t)cur; }
+            int k = -1;
+            for (int i = 0; i < a->n_resv; i++) if (a->resv[i] == card) k = i;
+            if (k < 0) return -1;
+            for (int i = k; i < 2; i++) a->resv[i] = a->resv[i + 1];
+            a->resv[2] = NONE;
+            a->n_resv--;
+            s->dealt[A.p] = (uint8_t)card;
+        }
+    } else if (A.type == T_BUY_AVAILABLE || A.type == T_BUY_RESERVE) {
+        for (int c = 0; c < 6; c++) { a->gems[c] += returned[c]; s->bank[c] -= returned[c]; }
+        if (A.type == T_BUY_AVAILABLE) {
+            int cur = s->dealt[A.p];
+            if (cur != NONE) { int t = card_tier(cur); s->deck[t][s->deck_n[t]++] = (uint8_t)cur; }
+            s->dealt[A.p] = (uint8_t)card;
+        } else {
+            a->resv[a->n_resv++] = (uint8_t)card;
+        }
+        a->cards[CARD[card].colour]--;
+        score -= CARD[card].points;
+    }
+    if (noble != NONE) {
+        s->nobles[s->n_nobles++] = (uint8_t)noble;
+        a->nobles_mask &= (uint16_t)~(1u << noble);
+        a->n_nobles--;
+        score -= 3;
+    }
+    a->turns--;
+    a->score = (uint8_t)(a->score + score);
+    a->passed = (A.type == T_PASS);
+    return 0;
+}

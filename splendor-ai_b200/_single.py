@@ -99,3 +99,16 @@ def observe(words, P, seat) -> np.ndarray:
     obs = torch.empty((1, 265), dtype=torch.float32, device=b["state"].device)
     nat.check(nat.lib().spl_observe(b["state"].data_ptr(), None, obs.data_ptr(), 1, P, _stream()), "spl_observe")
     return obs.cpu().numpy()[0]
+
+
+def undo(words, P, seat, index, card, noble, returned):
+    """generatePredecessor IN PLACE on words (spl_undo)."""
+    b = _buf(P)
+    _up(b, words)
+    d = b["state"].device
+    t = lambda v, dt: torch.tensor(v, dtype=dt, device=d)
+    seat_t, act_t, card_t, noble_t = t([seat], torch.int8), t([index], torch.int16), t([card], torch.uint8), t([noble], torch.uint8)
+    ret_t = t([list(returned)], torch.uint8)
+    nat.check(nat.lib().spl_undo(b["state"].data_ptr(), seat_t.data_ptr(), act_t.data_ptr(), card_t.data_ptr(), noble_t.data_ptr(),
+                                 ret_t.data_ptr(), 1, P, _stream()), "spl_undo")
+    words[:] = b["state"].cpu().numpy().view(np.uint32).reshape(-1)

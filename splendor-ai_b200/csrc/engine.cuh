@@ -803,6 +803,85 @@ __device__ __forceinline__ int apply_action(Env<P> &e, const Choice &ch, const D
     return score;
 }
 
+// generatePredecessor (splendor_model.py:156-220): undo ALL_ACTIONS[idx] for `seat`.  `card` = the card that was bought
+// or reserved, `noble` = the noble id that was claimed (NONE8 if none), `returned` = the action's returned_gems (g6; for
+// buys the payment).  The reference's quirks are kept: the noble and an un-bought reserved card are APPENDED to their
+// lists, the card that had been dealt into the slot goes back on top of its deck, `passed` comes from the undone action.
+// The reference keeps the seat to move in the rule object; the packed state carries it, so it is set back to `seat`.
+template <int P>
+__device__ __forceinline__ void undo_action(Env<P> &e, const Tables &T, int seat, int idx, uint32_t card, uint32_t noble, uint32_t returned)
+{
+    uint32_t g = e.pg[0], cd = e.pc[0], rv = e.pr[0], pi = e.pi[0];
+#pragma unroll
+    for (int p = 1; p < P; p++)
+        if (seat == p) { g = e.pg[p]; cd = e.pc[p]; rv = e.pr[p]; pi = e.pi[p]; }
+    int type = T_PASS, slot = 0, score = 0;
+    uint32_t C = 0, R = 0;
+    if (idx >= BASE_BUY_AVAILABLE) { type = T_BUY_AVAILABLE; slot = (idx - BASE_BUY_AVAILABLE) / 6; R = returned; }
+    else if (idx >= BASE_BUY_RESERVE) { type = T_BUY_RESERVE; R = returned; }
+    else if (idx >= BASE_DIFF) {
+        const int r = idx - BASE_DIFF;
+        int ci, rem, V;
+        if (r < 180) { ci = r / 36; rem = r % 36; V = 6; }
+        else if (r < 1080) { ci = 5 + (r - 180) / 90; rem = (r - 180) % 90; V = 15; }
+        else { ci = 15 + (r - 1080) / 120; rem = (r - 1080) % 120; V = 20; }
+        type = T_DIFF; C = T.combo_c[ci]; R = T.ret_diff[T.combo_off[ci] + rem % V];
+    } else if (idx >= BASE_SAME) {
+        const int r = idx - BASE_SAME, col = r / 126;
+        type = T_SAME; C = 2u << (5 * field_of_normal(col)); R = T.ret_same[col * 21 + r % 21];
+    } else if (idx >= BASE_RESERVE) {
+        const int r = idx - BASE_RESERVE, v = r % 7;
+        type = T_RESERVE; slot = r / 42;
+        if (v >= 1) C = 1u << YSH;
+        if (v >= 2) R = 1u << (5 * field_of_normal(v - 2));
+    }
+    g = g - C + R;
+    e.bank = e.bank + C - R;
+    if (type == T_RESERVE || type == T_BUY_AVAILABLE) {
+        const int tier = slot >> 2, col = slot & 3;
+        uint32_t w = tier == 0 ? e.d[0] : (tier == 1 ? e.d[1] : e.d[2]);
+        const uint32_t cur = byte_of(w, col);
+        if (cur != NONE8) {  // back on top of its deck
+            if (e.meta & META_EXPLICIT) e.k[0] += 1u << (8 * tier);
+            else {
+                const uint32_t pos = cur - (tier == 0 ? 0u : (tier == 1 ? 40u : 70u));
+                if (tier == 0 && pos < 32) e.k[0] |= 1u << pos;
+                else if (tier == 0) e.k[2] |= 1u << (20 + pos - 32);
+                else if (tier == 1) e.k[1] |= 1u << pos;
+                else e.k[2] |= 1u << pos;
+            }
+        }
+        w = set_byte(w, col, card);
+        if (tier == 0) e.d[0] = w; else if (tier == 1) e.d[1] = w; else e.d[2] = w;
+        if (type == T_RESERVE) {  // agent.cards["yellow"].remove(card)
+            const uint32_t list = rv & 0x00FFFFFFu;
+            const uint32_t sh = byte_of(list, 0) == card ? 0u : (byte_of(list, 1) == card ? 8u : 16u);
+            rv = (rv & 0xFF000000u) | (list & ((1u << sh) - 1u)) | ((list >> (sh + 8u)) << sh) | 0x00FF0000u;
+        }
+    } else if (type == T_BUY_RESERVE) {
+        rv = set_byte(rv, __popc(~rv & 0x00808080u), card);  // appended, not re-inserted at its old index
+    }
+    if (type >= T_BUY_RESERVE) {
+        const uint32_t info = T.card[card & 127u].y;
+        cd -= 1u << (info & 31u);
+        score -= (int)((info >> 5) & 7u);
+    }
+    if (noble != NONE8) {
+        int count = 0;  // board.nobles.append(noble): first free nibble
+#pragma unroll
+        for (int k = 0; k < 5; k++) count += ((e.meta >> (4 * k)) & 15u) != 15u;
+        e.meta = (e.meta & ~(15u << (4 * count))) | (noble << (4 * count));
+        pi &= ~(1u << (16 + noble));
+        score -= 3;
+    }
+    rv += (uint32_t)score << 24;
+    pi = ((pi - 1u) & ~(1u << 26)) | (type == T_PASS ? 1u << 26 : 0u);
+    e.meta = (e.meta & ~(3u << 20)) | ((uint32_t)seat << 20);  // the undone agent is to move again (inverse of apply_action)
+#pragma unroll
+    for (int p = 0; p < P; p++)
+        if (seat == p) { e.pg[p] = g; e.pc[p] = cd; e.pr[p] = rv; e.pi[p] = pi; }
+}
+
 template <int P>
 __device__ __forceinline__ int game_ends(const Env<P> &e, uint32_t flags)
 {

@@ -216,6 +216,23 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(uint4 *state, const uint8_t
 }
 
 template <int P>
+__global__ void __launch_bounds__(BLOCK) undo_kernel(uint4 *state, const int8_t *seat, const int16_t *action, const uint8_t *card,
+                                                     const uint8_t *noble, const uint8_t *returned, int64_t N)
+{
+    __shared__ Tables sT;
+    stage_tables(sT);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || action[i] < 0) return;
+    Env<P> e;
+    load_env(e, state, N, i);
+    uint32_t r = 0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) r |= (uint32_t)returned[i * 6 + c] << (5 * field_of_colour_id(c));
+    undo_action(e, sT, (int)seat[i], (int)action[i], (uint32_t)card[i], (uint32_t)noble[i], r);
+    store_env(e, state, N, i);
+}
+
+template <int P>
 __global__ void __launch_bounds__(BLOCK) final_scores_kernel(const uint4 *state, int8_t *score2, uint8_t *outcome,
                                                              uint8_t *end_kind, int64_t N, uint32_t flags)
 {
@@ -253,7 +270,8 @@ __device__ __forceinline__ void tile_store_obs(const uint8_t *tile, float *out, 
     for (int j = warp; j < n; j += TB / 32) {
         const uint8_t *row = tile + j * row_stride_bytes;
         float *dst = out + (int64_t)j * SPL_OBS_SIZE;
-        for (int w = lane; w < SPL_OBS_SIZE; w += 32) dst[w] = obs_entry(row, w, g_log1p_bits);
+        dst[lane] = obs_entry(row, lane, g_log1p_bits);  // the three special entries (turns, variance, log table) are all < 32
+        for (int w = lane + 32; w < SPL_OBS_SIZE; w += 32) dst[w] = (float)row[w];
     }
 }
 // rows [0, n) of `row_words` used words (row stride `row_stride` in the tile) -> out[0 .. n*row_words)
@@ -498,6 +516,17 @@ int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_ga
     if (N == 0) return SPL_OK;
     DISPATCH_P(P, step_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
                       (uint4 *)state, decks, seed, first_game, game_ids, action, reward, done, illegal, N, flags));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_undo(void *state, const int8_t *seat, const int16_t *action, const uint8_t *card, const uint8_t *noble,
+             const uint8_t *returned, int64_t N, int P, void *stream)
+{
+    if (!state || !seat || !action || !card || !noble || !returned || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    DISPATCH_P(P, undo_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>((uint4 *)state, seat, action, card, noble, returned, N));
     CK(cudaGetLastError());
     return SPL_OK;
 }

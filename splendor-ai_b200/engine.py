@@ -102,6 +102,15 @@ class BatchedSplendor:
                                         _ptr(done), _ptr(illegal), self.N, self.P, self.flags, _stream(self.device)), "spl_step")
         return reward, done, illegal
 
+    def undo(self, seat: torch.Tensor, actions: torch.Tensor, card: torch.Tensor, noble: torch.Tensor, returned: torch.Tensor):
+        """generatePredecessor for one action per env (see spl_undo): seat int8, action int16 (<0 = skip), card / noble
+        uint8 ids (255 = none), returned uint8 [N,6] by colour id."""
+        t = lambda x, dt: x.to(device=self.device, dtype=dt).contiguous()
+        s, a, c, n, r = t(seat, torch.int8), t(actions, torch.int16), t(card, torch.uint8), t(noble, torch.uint8), t(returned, torch.uint8)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_undo(_ptr(self.state), _ptr(s), _ptr(a), _ptr(c), _ptr(n), _ptr(r), self.N, self.P,
+                                        _stream(self.device)), "spl_undo")
+
     def observe(self, seat: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
         """extract_metrics_with_cards(...).astype(float32) -> [N, 265]; seat: int8 per env (None = seat to move)."""
         obs = out if out is not None else torch.empty((self.N, OBS_SIZE), dtype=torch.float32, device=self.device)

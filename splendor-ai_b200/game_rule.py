@@ -98,6 +98,7 @@ class SplendorState(template.GameState):
         self._noble_tuples = [[] for _ in range(num_agents)]
         self._traces = [AgentTrace(i) for i in range(num_agents)]
         self._last_action = [None] * num_agents
+        self._applied = []  # (agent_id, ALL_ACTIONS index) of every successor, so a predecessor can be taken in LIFO order
         self.agent_to_move = 0
         self._refresh()
 
@@ -225,6 +226,28 @@ class SplendorGameRule(template.GameRule):
             state._noble_tuples[agent_id].append(act["noble"])
         state._traces[agent_id].action_reward.append((act, reward))
         state._last_action[agent_id] = act
+        state._applied.append((agent_id, int(idx)))
+        state._refresh()
+        return state
+
+    def generatePredecessor(self, state, action, agent_id):
+        """Undo `action` of `agent_id` (splendor_model.py:156-220), most recent first as search agents do
+        (agents/our_agents/minmax.py:43-88).  Runs the undo kernel; the reference's list-order quirks are kept."""
+        from . import _single
+
+        if not state._applied or state._applied[-1][0] != agent_id:
+            raise ValueError("generatePredecessor must undo the most recent action of that agent")
+        _, idx = state._applied.pop()
+        card = CARD_ID[action["card"].code] if action.get("card") is not None else NONE
+        noble = NOBLE_ID[action["noble"][0]] if action.get("noble") is not None else NONE
+        returned = [int((action.get("returned_gems") or {}).get(c, 0)) for c in _COLS]
+        _single.undo(state._words, self.num_of_agent, agent_id, idx, card, noble, returned)
+        if action["type"].startswith("buy"):
+            state._bought[agent_id][action["card"].colour].remove(action["card"])
+        if action.get("noble") is not None:
+            state._noble_tuples[agent_id].remove(action["noble"])
+        state._traces[agent_id].action_reward.pop()
+        state._last_action[agent_id] = action
         state._refresh()
         return state
 

@@ -121,6 +121,15 @@ template <int P> static int t_step(uint32_t *w, const uint8_t *lists, uint64_t s
     *done = game_ends(e, flags);
     return bad;
 }
+template <int P> static int t_undo(uint32_t *w, int seat, int idx, int card, int noble, const uint8_t *returned)
+{
+    Env<P> e; ld(e, w);
+    uint32_t r = 0;
+    for (int c = 0; c < 6; c++) r |= (uint32_t)returned[c] << (5 * field_of_colour_id(c));
+    undo_action(e, T, seat, idx, (uint32_t)card, (uint32_t)noble, r);
+    st(e, w);
+    return 0;
+}
 template <int P> static int t_observe(const uint32_t *w, int seat, float *o)
 {
     Env<P> e; ld(e, w);
@@ -178,6 +187,7 @@ int sim_legal_member(const uint32_t *w, int P, uint16_t *out) { DISPATCH(P, retu
 int sim_mask(const uint32_t *w, int P, int seat, uint32_t *mask) { DISPATCH(P, return t_mask<PP>(w, seat, mask)); return -1; }
 int sim_step(uint32_t *w, const uint8_t *lists, uint64_t seed, uint64_t game, int P, int idx, uint32_t flags, int *reward, int *done)
 { DISPATCH(P, return t_step<PP>(w, lists, seed, game, idx, flags, reward, done)); return -1; }
+int sim_undo(uint32_t *w, int P, int seat, int idx, int card, int noble, const uint8_t *returned) { DISPATCH(P, return t_undo<PP>(w, seat, idx, card, noble, returned)); return -1; }
 int sim_observe(const uint32_t *w, int P, int seat, float *o) { DISPATCH(P, return t_observe<PP>(w, seat, o)); return -1; }
 int sim_scores(const uint32_t *w, int P, uint32_t flags, int *score2, int *outcome, int *kind) { DISPATCH(P, return t_scores<PP>(w, flags, score2, outcome, kind)); return -1; }
 int sim_playout(uint32_t *w, int fresh, const uint8_t *lists, uint64_t seed, uint64_t game, int P, uint32_t flags, int max_steps,

@@ -26,6 +26,7 @@ def lib():
         _lib.sim_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib.sim_step.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint32,
                                   C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _lib.sim_undo.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib.sim_observe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib.sim_scores.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         _lib.sim_playout.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_int,
@@ -84,6 +85,10 @@ class Sim:
         r, d = C.c_int(), C.c_int()
         bad = lib().sim_step(_p(self.w), _p(self.lists), self.seed, self.game, self.P, int(idx), flags, C.byref(r), C.byref(d))
         return bad, r.value, d.value
+
+    def undo(self, seat, idx, card, noble, returned):
+        r = np.ascontiguousarray(returned, np.uint8)
+        lib().sim_undo(_p(self.w), self.P, int(seat), int(idx), int(card), int(noble), _p(r))
 
     def observe(self, seat):
         out = np.zeros(265, np.float32)

@@ -198,3 +198,49 @@ def test_vec_env_rollout_with_auto_reset(oracle):
             r = int(oracle.philox(seed, track + N, sum(s.pl[i].turns for i in range(P)), 0)[0])
             oracle.step(s, int(legal[(r * len(legal)) >> 32]))
     assert len(trace) > 10
+
+
+def test_tally_matches_the_reference_runner_rules():
+    """win = unique best score, tie = shared best, else loss (general_game_runner.py:416-430)."""
+    from splendor_ai_b200.game import tally
+
+    t = tally([[15, 12], [16.5, 16], [15, 15], [3, 18], [15.5, 15.5]])
+    assert t["wins"] == [2, 1] and t["ties"] == [2, 2] and t["loses"] == [1, 2]
+    assert t["total_scores"] == [65.0, 76.5] and t["win_rates"] == [40.0, 20.0]
+
+
+@pytest.mark.gpu
+def test_game_loop_history_and_replayer():
+    """Game.Run with host RandomAgents: the reference's history dict, then GameReplayer reproduces the final state."""
+    from splendor_ai_b200 import game_rule as G
+    from splendor_ai_b200 import template
+    from splendor_ai_b200.game import Game, GameReplayer
+    from splendor_ai_b200.state import snapshots
+
+    g = Game(G.SplendorGameRule, [template.RandomAgent(0), template.RandomAgent(1)], 2, seed=21, agents_namelist=["a", "b"])
+    h = g.Run()
+    assert set(h) >= {"actions", "seed", "num_of_agent", "agents_namelist", "warning_positions", "warning_limit", "scores"}
+    assert h["seed"] == 21 and len(h["actions"]) > 20 and set(h["scores"]) == {0, 1}
+    for i, item in enumerate(h["actions"]):
+        ((idx, info),) = item.items()
+        assert idx == i and info["agent_id"] == i % 2 and "type" in info["action"]
+    final = g.game_rule.current_game_state
+    assert max(a.score for a in final.agents) >= 15 or all(a.passed for a in final.agents)
+    assert h["scores"][0] == g.game_rule.calScore(final, 0)
+    r = GameReplayer(G.SplendorGameRule, h)
+    replayed = r.Run()
+    assert np.array_equal(snapshots(replayed._words.reshape(-1, 1, 4), 2), snapshots(final._words.reshape(-1, 1, 4), 2))
+
+
+@pytest.mark.gpu
+def test_random_tournament_statistics(oracle):
+    """The batched `splendor -m N` for random agents: the runner's matches dict, equal to the oracle's tallies."""
+    from splendor_ai_b200.game import run_random_tournament
+
+    N, seed = 5000, 4
+    m = run_random_tournament(N, 2, seed=seed)
+    sc, st, ctr = oracle.playout_many(seed, 0, N, 2, False, 1000, nthreads=os.cpu_count() or 1)
+    assert m["wins"] == [int(ctr[2]), int(ctr[3])] and m["ties"] == [int(ctr[6]), int(ctr[7])]
+    assert m["loses"] == [N - m["wins"][i] - m["ties"][i] for i in range(2)]
+    assert m["total_scores"] == (sc.astype(np.float64).sum(0) / 2).tolist()
+    assert abs(sum(m["win_rates"]) + 100.0 * m["ties"][0] / N - 100.0) < 1e-9 and m["succ"]
