@@ -999,7 +999,7 @@ __device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &
         for (int col = 0; col < 5; col++) {
             const uint32_t vs = (c.A4 >> field_of_normal(col) & 1u) ? same_variant_bits(T, c, col, e2) : 0u;
             or_bits64(m, BASE_SAME + 126 * col, times_nobles(vs, 21, np_lo));
-            or_bits64(m, BASE_SAME + 126 * col + 63, times_nobles(vs, 21, np_hi));
+            if (np_hi) or_bits64(m, BASE_SAME + 126 * col + 63, times_nobles(vs, 21, np_hi));  // nobles at list position >= 2: rare
             any_bits |= vs;
         }
     }
@@ -1013,7 +1013,7 @@ __device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &
         if (L == 1) or_bits64(m, base, times_nobles(vd, V, np_lo) | times_nobles(vd, V, np_hi) << 18);
         else {
             or_bits64(m, base, times_nobles(vd, V, np_lo));
-            or_bits64(m, base + 3 * V, times_nobles(vd, V, np_hi));
+            if (np_hi) or_bits64(m, base + 3 * V, times_nobles(vd, V, np_hi));
         }
         any_bits |= vd;
     }
@@ -1090,9 +1090,11 @@ __device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T
         const uint32_t turns = sum == 0 ? 0u : max((sum + 2u) / 3u, mx);  // features.py:124-135
         o[(s < 12 ? 30 : 54 - 12) + s] = (uint8_t)sum;
         o[(s < 12 ? 42 : 57 - 12) + s] = (uint8_t)turns;
-#pragma unroll
-        for (int f = 0; f < 6; f++)
-            if (f != 2 && sh == 5u * f) best[f] = insert_sorted4(best[f], sum);
+        {  // insert into this card's colour tuple only: select, insert, write back
+            const uint32_t t = insert_sorted4(sh == 0u ? best[0] : (sh == 5u ? best[1] : (sh == 15u ? best[3] : (sh == 20u ? best[4] : best[5]))), sum);
+            best[0] = sh == 0u ? t : best[0]; best[1] = sh == 5u ? t : best[1]; best[3] = sh == 15u ? t : best[3];
+            best[4] = sh == 20u ? t : best[4]; best[5] = sh == 25u ? t : best[5];
+        }
         // vectorize_card (features.py:377-413): one-hot over sklearn's alphabetical categories black, blue, green, red,
         // white, yellow; the cost in alphabetical order black, blue, green, red, white; deck_id; points
         uint8_t *v = o + 70 + 13 * s;
