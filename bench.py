@@ -289,7 +289,12 @@ def run_b200(args):
     D.allreduce_counters(e2e_steps)
     e2e_value = int(e2e_steps.item()) / e2e_s
 
-    other = other_kernels(pkg, dev) if rank == 0 else None
+    other = None
+    if rank == 0:
+        try:
+            other = other_kernels(pkg, dev)
+        except Exception as exc:  # informational section: never fail the headline measurement because of it
+            other = {"error": repr(exc)}
     D.barrier()
     D.shutdown()
     if rank != 0:

@@ -167,10 +167,21 @@ PLAN = [
                     (4, "reserve", False, 1)]),
 ]
 
+# a second batch with other seeds (added later in round 1; the first three files are left untouched)
+PLAN_B = [
+    ("replays_2p_b", [(2, "random", False, 20), (2, "greedy", False, 10), (2, "hoard", False, 6), (2, "reserve", False, 4),
+                      (2, "random", True, 6), (2, "greedy", True, 4)]),
+    ("replays_3p_b", [(3, "random", False, 6), (3, "greedy", False, 4), (3, "hoard", True, 2)]),
+    ("replays_4p_b", [(4, "random", False, 8), (4, "greedy", False, 6), (4, "hoard", False, 3), (4, "reserve", True, 2)]),
+]
+
 if __name__ == "__main__":
     assert os.environ.get("PYTHONHASHSEED") == "0", "run with PYTHONHASHSEED=0 for reproducible action choices"
     seed = 1000
-    for name, groups in PLAN:
+    plan = PLAN
+    if len(sys.argv) > 1 and sys.argv[1] == "b":
+        plan, seed = PLAN_B, 5000
+    for name, groups in plan:
         t0, games = time.time(), []
         for P, policy, limit, n in groups:
             for _ in range(n):

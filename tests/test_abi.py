@@ -56,4 +56,4 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src.lower() or f == "__init__.py" and False, os.path.join(dirpath, f)
+                assert "oracle" not in src.lower(), os.path.join(dirpath, f)

@@ -37,7 +37,7 @@ def _check_decision(sim, orc, oracle, where):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (where, seat, np.nonzero(a != b))
 
 
-@pytest.mark.parametrize("name", ["replays_2p", "replays_3p", "replays_4p"])
+@pytest.mark.parametrize("name", ["replays_2p", "replays_3p", "replays_4p", "replays_2p_b", "replays_3p_b", "replays_4p_b"])
 def test_reference_recordings_through_device_code(oracle, name):
     """Injected reference deck orders + recorded action traces: every state, legal set and observation identical."""
     for gi, g in enumerate(load_replays(name)):

@@ -44,7 +44,7 @@ def test_reset_matches_oracle(pkg, oracle, P):
         assert pkg.state.remaining_deck_sets(u["deck_masks"][e]) == s.remaining_deck_sets(), e
 
 
-@pytest.mark.parametrize("name", ["replays_2p", "replays_3p", "replays_4p"])
+@pytest.mark.parametrize("name", ["replays_2p", "replays_3p", "replays_4p", "replays_2p_b", "replays_3p_b", "replays_4p_b"])
 def test_reference_recordings_replayed_on_gpu(pkg, name):
     """The REFERENCE's own recorded games (deck orders injected, recorded actions replayed): every legal mask,
     observation, reward, terminal flag, state and final score identical to what the Python engine produced."""

@@ -9,7 +9,7 @@ import pytest
 from conftest import load_replays
 
 
-@pytest.mark.parametrize("name", ["replays_2p", "replays_3p", "replays_4p"])
+@pytest.mark.parametrize("name", ["replays_2p", "replays_3p", "replays_4p", "replays_2p_b", "replays_3p_b", "replays_4p_b"])
 def test_oracle_replays_reference_games(oracle, name):
     games = load_replays(name)
     n_steps = 0
