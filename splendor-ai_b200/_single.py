@@ -78,11 +78,12 @@ def step(words, deck_lists, P, seat, index):
     return int(res[0].astype(np.int8)), bool(res[2])
 
 
-def game_ends(words, P, current_agent_index) -> int:
+def game_ends(words, P, current_agent_index, limit_rounds=False) -> int:
     b = _buf(P)
     _up(b, words, current_agent_index)
     o = b["out"]
-    nat.check(nat.lib().spl_final_scores(b["state"].data_ptr(), None, None, o[0:1].data_ptr(), 1, P, 0, _stream()), "spl_final_scores")
+    nat.check(nat.lib().spl_final_scores(b["state"].data_ptr(), None, None, o[0:1].data_ptr(), 1, P,
+                                         nat.F_LIMIT_ROUNDS if limit_rounds else 0, _stream()), "spl_final_scores")
     return int(o[0].item())
 
 

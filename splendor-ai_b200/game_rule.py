@@ -252,12 +252,10 @@ class SplendorGameRule(template.GameRule):
         return state
 
     def gameEnds(self):
-        st = self.current_game_state
-        if self.LIMIT_ROUNDS and all(len(a.agent_trace.action_reward) == ROUNDS_LIMIT for a in st.agents):
-            return True
         from . import _single
 
-        return _single.game_ends(st._words, self.num_of_agent, self.current_agent_index) != 0
+        st = self.current_game_state
+        return _single.game_ends(st._words, self.num_of_agent, self.current_agent_index, self.LIMIT_ROUNDS) != 0
 
     def calScore(self, game_state, agent_id):
         from . import _single
