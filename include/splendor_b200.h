@@ -106,6 +106,18 @@ int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_ga
              const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal, int64_t N, int P, uint32_t flags,
              void *stream);
 
+/* One-ply expansion for search-style agents (what minimax / the GA agent do one action at a time with
+ * generateSuccessor + generatePredecessor, agents/our_agents/minmax.py:43-88, genetic_algorithm_agent.py:93-96):
+ * spl_count_legal writes len(getLegalActions(state, seat to move)) per env; the caller turns the counts into exclusive
+ * prefix sums offsets[0..N] (offsets[N] = M); spl_expand then writes every successor: child j of env e (its j-th legal
+ * action in ascending ALL_ACTIONS order) becomes env offsets[e]+j of an M-env batch in the packed layout, with the action
+ * index, the acting agent's reward and the parent env in the optional side arrays.  Children of explicit-deck envs read
+ * the parent's deck list: pass decks gathered by out_parent to later calls on the children. */
+int spl_count_legal(const void *state, int32_t *counts, int64_t N, int P, void *stream);
+int spl_expand(const void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
+               const int64_t *offsets, void *out_state, int16_t *out_action, int8_t *out_reward, int32_t *out_parent, int64_t N,
+               int64_t M, int P, void *stream);
+
 /* SplendorGameRule.generatePredecessor(state, action, agent_id) (splendor_model.py:156-220): undo one action per env for
  * seat[e].  Besides the ALL_ACTIONS index the undo needs what the reference reads from the action dict: card[e] = id of
  * the card that was bought / reserved (0xFF otherwise), noble[e] = id of the noble that was claimed (0xFF if none),

@@ -232,6 +232,53 @@ __global__ void __launch_bounds__(BLOCK) undo_kernel(uint4 *state, const int8_t 
     store_env(e, state, N, i);
 }
 
+// ---------------------------------------------------------------------------------------------- one-ply expansion
+template <int P>
+__global__ void __launch_bounds__(BLOCK) count_legal_kernel(const uint4 *state, int32_t *counts, int64_t N)
+{
+    __shared__ Tables sT;
+    stage_tables(sT);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Env<P> e;
+    load_env(e, state, N, i);
+    Ctx c;
+    FamilyCounts f;
+    make_ctx(e, sT, c);
+    const int total = count_legal(e, sT, c, f);
+    counts[i] = total ? total : c.nS;
+}
+
+// children of env i go to columns offsets[i] .. offsets[i+1]-1 of the M-env output batch, in ascending ALL_ACTIONS order
+template <int P>
+__global__ void __launch_bounds__(BLOCK) expand_kernel(const uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+                                                       const uint64_t *game_ids, const int64_t *offsets, uint4 *out_state,
+                                                       int16_t *out_action, int8_t *out_reward, int32_t *out_parent, int64_t N, int64_t M)
+{
+    __shared__ Tables sT;
+    stage_tables(sT);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Env<P> e;
+    load_env(e, state, N, i);
+    Ctx c;
+    FamilyCounts f;
+    make_ctx(e, sT, c);
+    const int total = count_legal(e, sT, c, f), n = total ? total : c.nS;
+    const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
+    const int64_t base = offsets[i];
+    for (int k = 0; k < n && base + k < M; k++) {
+        Choice ch;
+        select_legal(e, sT, c, f, total, k, ch);
+        Env<P> child = e;
+        const int rew = apply_action(child, ch, src);
+        store_env(child, out_state, M, base + k);
+        if (out_action) out_action[base + k] = (int16_t)ch.idx;
+        if (out_reward) out_reward[base + k] = (int8_t)rew;
+        if (out_parent) out_parent[base + k] = (int32_t)i;
+    }
+}
+
 template <int P>
 __global__ void __launch_bounds__(BLOCK) final_scores_kernel(const uint4 *state, int8_t *score2, uint8_t *outcome,
                                                              uint8_t *end_kind, int64_t N, uint32_t flags)
@@ -516,6 +563,30 @@ int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_ga
     if (N == 0) return SPL_OK;
     DISPATCH_P(P, step_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
                       (uint4 *)state, decks, seed, first_game, game_ids, action, reward, done, illegal, N, flags));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_count_legal(const void *state, int32_t *counts, int64_t N, int P, void *stream)
+{
+    if (!state || !counts || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    DISPATCH_P(P, count_legal_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>((const uint4 *)state, counts, N));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_expand(const void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
+               const int64_t *offsets, void *out_state, int16_t *out_action, int8_t *out_reward, int32_t *out_parent, int64_t N,
+               int64_t M, int P, void *stream)
+{
+    if (!state || !offsets || !out_state || N < 0 || M < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0 || M == 0) return SPL_OK;
+    DISPATCH_P(P, expand_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
+                      (const uint4 *)state, decks, seed, first_game, game_ids, offsets, (uint4 *)out_state, out_action, out_reward,
+                      out_parent, N, M));
     CK(cudaGetLastError());
     return SPL_OK;
 }

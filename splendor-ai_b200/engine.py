@@ -102,6 +102,38 @@ class BatchedSplendor:
                                         _ptr(done), _ptr(illegal), self.N, self.P, self.flags, _stream(self.device)), "spl_step")
         return reward, done, illegal
 
+    def count_legal(self) -> torch.Tensor:
+        """len(getLegalActions(state, seat to move)) per env (int32 [N])."""
+        counts = torch.empty(self.N, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_count_legal(_ptr(self.state), _ptr(counts), self.N, self.P, _stream(self.device)), "spl_count_legal")
+        return counts
+
+    def expand(self):
+        """Every successor of every env (one ply): returns (children: BatchedSplendor of M envs, action int16 [M], reward int8 [M],
+        parent int32 [M], offsets int64 [N+1]); children of env e are envs offsets[e]..offsets[e+1]-1 in ascending action order."""
+        counts = self.count_legal()
+        offsets = torch.zeros(self.N + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(counts, 0, out=offsets[1:])
+        M = int(offsets[-1].item())
+        child = BatchedSplendor.__new__(BatchedSplendor)
+        child.lib, child.N, child.P, child.device = self.lib, M, self.P, self.device
+        child.seed, child.first_game, child.flags = self.seed, self.first_game, self.flags
+        child.state = torch.empty(state_shape(M, self.P), dtype=torch.int32, device=self.device)
+        action = torch.empty(M, dtype=torch.int16, device=self.device)
+        reward = torch.empty(M, dtype=torch.int8, device=self.device)
+        parent = torch.empty(M, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_expand(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, _ptr(self.game_ids), _ptr(offsets),
+                                          _ptr(child.state), _ptr(action), _ptr(reward), _ptr(parent), self.N, M, self.P,
+                                          _stream(self.device)), "spl_expand")
+        idx = parent.to(torch.int64)
+        child.decks = None if self.decks is None else self.decks[idx].contiguous()
+        base_ids = self.game_ids if self.game_ids is not None else \
+            self.first_game + torch.arange(self.N, device=self.device, dtype=torch.int64)
+        child.game_ids = base_ids[idx].contiguous()
+        return child, action, reward, parent, offsets
+
     def undo(self, seat: torch.Tensor, actions: torch.Tensor, card: torch.Tensor, noble: torch.Tensor, returned: torch.Tensor):
         """generatePredecessor for one action per env (see spl_undo): seat int8, action int16 (<0 = skip), card / noble
         uint8 ids (255 = none), returned uint8 [N,6] by colour id."""

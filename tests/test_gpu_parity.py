@@ -292,3 +292,44 @@ def test_fuzzed_states_on_gpu(pkg, oracle, P):
             o2 = o.copy()
             assert illegal[e] == 0 and reward[e] == oracle.step(o2, int(act[e])), (P, e)
             assert done[e] == oracle.game_ends(o2, limit) and np.array_equal(sn[e], o2.snapshot()), (P, e)
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_one_and_two_ply_expansion(pkg, oracle, P):
+    """spl_count_legal + spl_expand: every successor of mid-game states (counter-based decks), then the successors'
+    successors, against the oracle stepping copies - the batched form of minimax's successor/predecessor walk."""
+    N, seed = 96, 11
+    eng = pkg.BatchedSplendor(N, P, seed=seed, first_game=50)
+    orcs = [oracle.init(P, *oracle.synth_game(seed, 50 + e, P)) for e in range(N)]
+    rng = np.random.default_rng(P)
+    for _ in range(24):  # advance to mid-game with random legal actions
+        act = np.array([rng.choice(oracle.legal(o)) if not oracle.game_ends(o, False) else -1 for o in orcs], np.int16)
+        eng.step(torch.from_numpy(act))
+        for o, a in zip(orcs, act):
+            if a >= 0:
+                oracle.step(o, int(a))
+    child, action, reward, parent, offsets = eng.expand()
+    action, reward, parent, offsets = (x.cpu().numpy() for x in (action, reward, parent, offsets))
+    counts = eng.count_legal().cpu().numpy()
+    sn = pkg.state.snapshots(child.state_numpy(), P)
+    kids = []
+    for e, o in enumerate(orcs):
+        legal = oracle.legal(o)
+        assert counts[e] == len(legal) == offsets[e + 1] - offsets[e]
+        for j, a in enumerate(legal):
+            m = offsets[e] + j
+            c = o.copy()
+            assert action[m] == a and parent[m] == e and reward[m] == oracle.step(c, int(a)), (e, j)
+            assert np.array_equal(sn[m], c.snapshot()), (e, j)
+            kids.append(c)
+    # second ply on the children (their lazily dealt cards must continue the parent's deck order)
+    grand, action2, _, parent2, offsets2 = child.expand()
+    action2, parent2, offsets2 = (x.cpu().numpy() for x in (action2, parent2, offsets2))
+    sn2 = pkg.state.snapshots(grand.state_numpy(), P)
+    for m in rng.choice(len(kids), size=min(300, len(kids)), replace=False):
+        legal = oracle.legal(kids[m])
+        assert offsets2[m + 1] - offsets2[m] == len(legal)
+        for j in (0, len(legal) - 1):
+            c = kids[m].copy()
+            oracle.step(c, int(legal[j]))
+            assert action2[offsets2[m] + j] == legal[j] and np.array_equal(sn2[offsets2[m] + j], c.snapshot()), (m, j)
