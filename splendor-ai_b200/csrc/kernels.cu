@@ -707,23 +707,50 @@ int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t 
     if (N == 0) return SPL_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     std::lock_guard<std::mutex> lock(g_stage_mu);
-    const size_t o_state = 0, o_decks = o_state + align256((size_t)N * (8 + 4 * P) * 4),
+    // The batch is cut into chunks that travel on separate internal streams: the H2D copy of chunk k+1 and the D2H copy
+    // of chunk k-1 overlap the kernels of chunk k (and the chunk kernels, latency-bound at this size, overlap each other).
+    constexpr int MAX_CHUNKS = 4;
+    static cudaStream_t side[MAX_CHUNKS] = {};
+    static cudaEvent_t ev_start = nullptr, ev_done[MAX_CHUNKS] = {};
+    if (!ev_start) {
+        CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        for (int c = 0; c < MAX_CHUNKS; c++) {
+            CK(cudaStreamCreateWithFlags(&side[c], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+        }
+    }
+    const int n_chunks = N >= 16384 ? MAX_CHUNKS : 1;
+    const int64_t per = (N + n_chunks - 1) / n_chunks;
+    const size_t W = (size_t)(8 + 4 * P) * 4;
+    const size_t o_state = 0, o_decks = o_state + align256((size_t)N * W) + 256 * MAX_CHUNKS,
                  o_nobles = o_decks + align256((size_t)N * SPL_DECK_BYTES), o_score = o_nobles + align256((size_t)N * 5),
                  o_steps = o_score + align256((size_t)N * P), o_kind = o_steps + align256((size_t)N * 2),
                  o_ctr = o_kind + align256((size_t)N), total = o_ctr + 256;
     if (int rc = g_stage.ensure(total)) return rc;
     char *b = (char *)g_stage.p;
-    CK(cudaMemcpyAsync(b + o_decks, deck_lists, (size_t)N * SPL_DECK_BYTES, cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(b + o_nobles, nobles, (size_t)N * 5, cudaMemcpyHostToDevice, stream));
     CK(cudaMemsetAsync(b + o_ctr, 0, 128, stream));
-    if (int rc = spl_inject(b + o_state, (const uint8_t *)(b + o_decks), (const uint8_t *)(b + o_nobles), N, P, stream)) return rc;
-    if (int rc = spl_playout_from(b + o_state, (const uint8_t *)(b + o_decks), seed, first_game, nullptr, N, P, flags, max_steps,
-                                  (int8_t *)(b + o_score), (int16_t *)(b + o_steps), (uint8_t *)(b + o_kind),
-                                  (int64_t *)(b + o_ctr), nullptr, 0, stream))
-        return rc;
-    if (score2) CK(cudaMemcpyAsync(score2, b + o_score, (size_t)N * P, cudaMemcpyDeviceToHost, stream));
-    if (steps) CK(cudaMemcpyAsync(steps, b + o_steps, (size_t)N * 2, cudaMemcpyDeviceToHost, stream));
-    if (end_kind) CK(cudaMemcpyAsync(end_kind, b + o_kind, (size_t)N, cudaMemcpyDeviceToHost, stream));
+    CK(cudaEventRecord(ev_start, stream));
+    size_t state_off = o_state;
+    for (int c = 0; c < n_chunks; c++) {
+        const int64_t lo = (int64_t)c * per, n = (lo + per <= N ? per : N - lo);
+        if (n <= 0) break;
+        cudaStream_t s = side[c];
+        CK(cudaStreamWaitEvent(s, ev_start, 0));
+        char *st = b + state_off;  // each chunk is its own chunk-major state batch of n envs
+        state_off += align256((size_t)n * W);
+        CK(cudaMemcpyAsync(b + o_decks + lo * SPL_DECK_BYTES, deck_lists + lo * SPL_DECK_BYTES, (size_t)n * SPL_DECK_BYTES, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b + o_nobles + lo * 5, nobles + lo * 5, (size_t)n * 5, cudaMemcpyHostToDevice, s));
+        if (int rc = spl_inject(st, (const uint8_t *)(b + o_decks + lo * SPL_DECK_BYTES), (const uint8_t *)(b + o_nobles + lo * 5), n, P, s)) return rc;
+        if (int rc = spl_playout_from(st, (const uint8_t *)(b + o_decks + lo * SPL_DECK_BYTES), seed, first_game + (uint64_t)lo, nullptr, n, P,
+                                      flags, max_steps, (int8_t *)(b + o_score) + lo * P, (int16_t *)(b + o_steps) + lo,
+                                      (uint8_t *)(b + o_kind) + lo, (int64_t *)(b + o_ctr), nullptr, 0, s))
+            return rc;
+        if (score2) CK(cudaMemcpyAsync(score2 + lo * P, b + o_score + lo * P, (size_t)n * P, cudaMemcpyDeviceToHost, s));
+        if (steps) CK(cudaMemcpyAsync(steps + lo, b + o_steps + lo * 2, (size_t)n * 2, cudaMemcpyDeviceToHost, s));
+        if (end_kind) CK(cudaMemcpyAsync(end_kind + lo, b + o_kind + lo, (size_t)n, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(ev_done[c], s));
+        CK(cudaStreamWaitEvent(stream, ev_done[c], 0));
+    }
     int64_t ctr[16];
     CK(cudaMemcpyAsync(ctr, b + o_ctr, 128, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
