@@ -344,7 +344,9 @@ __device__ __forceinline__ uint32_t deal(Env<P> &e, int tier, const DeckSrc &src
     else { lo = e.k[2] & 0xFFFFFu; size = 20; base = 70; }
     const int clo = __popc(lo), c = clo + __popc(hi);
     if (c == 0) return NONE8;
-    const uint32_t r = philox(src.seed, src.game, (uint32_t)(size - c), STREAM_DECK0 + tier).x;
+    const uint32_t d = (uint32_t)(size - c);  // draw number: word d&3 of Philox call d>>2 of this tier's stream
+    const uint4 r4 = philox(src.seed, src.game, d >> 2, STREAM_DECK0 + tier);
+    const uint32_t r = (d & 3u) == 0 ? r4.x : ((d & 3u) == 1 ? r4.y : ((d & 3u) == 2 ? r4.z : r4.w));
     int j = (int)__umulhi(r, (uint32_t)c), pos;
     if (j < clo) {
         pos = select_bit(lo, j);
@@ -379,13 +381,25 @@ __device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t gam
         list = (list & ~(15u << (4 * i))) | ((uint32_t)vj << (4 * i));
     }
     e.meta = list | ((uint32_t)(P - 2) << 22);
-    DeckSrc src{nullptr, seed, game};
-    e.d[0] = e.d[1] = e.d[2] = 0;
+    // the 12 initial deals: draws 0..3 of each tier are the four words of that tier's first Philox call
 #pragma unroll 1
-    for (int i = 0; i < 12; i++) {  // one copy of deal() in the binary: the reset runs once per game, the step loop 90 times
-        const int t = i >> 2;
-        const uint32_t card = deal(e, t, src) << (8 * (i & 3));
-        if (t == 0) e.d[0] |= card; else if (t == 1) e.d[1] |= card; else e.d[2] |= card;
+    for (int t = 0; t < 3; t++) {
+        const uint4 r4 = philox(seed, game, 0, STREAM_DECK0 + t);
+        const uint32_t rr4[4] = {r4.x, r4.y, r4.z, r4.w};
+        const int size = t == 0 ? 40 : (t == 1 ? 30 : 20), base = t == 0 ? 0 : (t == 1 ? 40 : 70);
+        uint32_t lo = t == 0 ? 0xFFFFFFFFu : (t == 1 ? 0x3FFFFFFFu : 0x000FFFFFu), hi = t == 0 ? 0xFFu : 0u, w = 0;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int clo = __popc(lo), j = (int)__umulhi(rr4[d], (uint32_t)(size - d));
+            const bool in_hi = j >= clo;
+            const int pos = select_bit(in_hi ? hi : lo, in_hi ? j - clo : j);
+            lo &= ~(in_hi ? 0u : 1u << pos);
+            hi &= ~(in_hi ? 1u << pos : 0u);
+            w |= (uint32_t)(base + pos + (in_hi ? 32 : 0)) << (8 * d);
+        }
+        if (t == 0) { e.d[0] = w; e.k[0] = lo; e.k[2] = (e.k[2] & 0xF00FFFFFu) | hi << 20; }
+        else if (t == 1) { e.d[1] = w; e.k[1] = lo; }
+        else { e.d[2] = w; e.k[2] = (e.k[2] & 0xFFF00000u) | lo; }
     }
 #pragma unroll
     for (int p = 0; p < P; p++) { e.pg[p] = 0; e.pc[p] = 0; e.pr[p] = 0x00FFFFFFu; e.pi[p] = 0; }
@@ -565,6 +579,7 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
     const uint32_t eff = (c.gems & ~(31u << YSH)) + c.cards;    // gems + bought cards per colour (<= 14)
     const uint32_t cap = ((c.cards + 9u * ONES6) & H6) | (16u << YSH);  // guard bit set where 7 cards of the colour are owned (+ filler)
     uint32_t lo = 0, hi = 0;
+#ifndef SPL_ROLL_BUY  // unrolled: 3 % faster at 65,536 games per launch; rolled: 2 % faster at 2^20 (smaller code)
 #pragma unroll
     for (int s = 0; s < 15; s++) {
         const uint32_t w = s < 12 ? e.d[s >> 2] : c.resv;
@@ -575,6 +590,27 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
         const uint32_t cnt = ok ? (uint32_t)max(__popc(c.S | ((c.near >> sh) & 31u)), 1) : 0u;
         if (s < 8) lo |= cnt << (4 * s); else hi |= cnt << (4 * (s - 8));
     }
+#else
+    // four groups of four slots (three board rows, then the reserved list whose 4th byte is forced empty): rolled to keep
+    // the step loop inside the instruction cache (profiles/r1h: no_instruction stalls when warps are spread over
+    // reset / step / finalize code)
+#pragma unroll 1
+    for (int g = 0; g < 4; g++) {
+        const uint32_t w = g == 0 ? e.d[0] : (g == 1 ? e.d[1] : (g == 2 ? e.d[2] : (c.resv | 0xFF000000u)));
+        uint32_t gw = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint2 cw = T.card[(w >> (8 * b)) & 127u];
+            const uint32_t sh = cw.y & 31u;
+            const uint32_t wild = hsum6_small(satsub6(cw.x, eff));   // max(cost - cards - gems, 0) summed = wilds needed
+            const bool ok = wild <= (uint32_t)c.yellow && !((cap >> sh) & 16u);
+            gw |= (ok ? (uint32_t)max(__popc(c.S | ((c.near >> sh) & 31u)), 1) : 0u) << (4 * b);
+        }
+        gw <<= 16 * (g & 1);
+        lo |= g < 2 ? gw : 0u;
+        hi |= g < 2 ? 0u : gw;
+    }
+#endif
     f.buy_lo = lo; f.buy_hi = hi;
     f.bav = (int)(nibble_sum(lo) + nibble_sum(hi & 0xFFFFu));
     f.bres = (int)nibble_sum(hi >> 16);
