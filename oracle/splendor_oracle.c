@@ -624,9 +624,9 @@ void orc_synth_game(uint64_t seed, uint64_t game, int P, uint8_t *deck_lists, ui
         uint8_t remaining[40];
         for (int i = 0; i < n; i++) remaining[i] = (uint8_t)i; /* ascending positions still in the deck */
         for (int d = 0; d < n; d++) {
-            uint32_t w[4]; /* draw d uses word d&3 of Philox call d>>2 of this tier's stream */
-            orc_philox(seed, game, (uint32_t)(d >> 2), (uint32_t)(STREAM_DECK0 + t), w);
-            int c = n - d, j = (int)mulhi(w[d & 3], (uint32_t)c);
+            uint32_t w[4];
+            orc_philox(seed, game, (uint32_t)d, (uint32_t)(STREAM_DECK0 + t), w);
+            int c = n - d, j = (int)mulhi(w[0], (uint32_t)c);
             int pos = remaining[j];
             memmove(remaining + j, remaining + j + 1, (size_t)(c - 1 - j));
             deck_lists[TIER_BASE[t] + (n - 1 - d)] = (uint8_t)(TIER_BASE[t] + pos); /* d-th deal pops from the end */

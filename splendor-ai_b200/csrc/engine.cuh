@@ -344,9 +344,7 @@ __device__ __forceinline__ uint32_t deal(Env<P> &e, int tier, const DeckSrc &src
     else { lo = e.k[2] & 0xFFFFFu; size = 20; base = 70; }
     const int clo = __popc(lo), c = clo + __popc(hi);
     if (c == 0) return NONE8;
-    const uint32_t d = (uint32_t)(size - c);  // draw number: word d&3 of Philox call d>>2 of this tier's stream
-    const uint4 r4 = philox(src.seed, src.game, d >> 2, STREAM_DECK0 + tier);
-    const uint32_t r = (d & 3u) == 0 ? r4.x : ((d & 3u) == 1 ? r4.y : ((d & 3u) == 2 ? r4.z : r4.w));
+    const uint32_t r = philox(src.seed, src.game, (uint32_t)(size - c), STREAM_DECK0 + tier).x;
     int j = (int)__umulhi(r, (uint32_t)c), pos;
     if (j < clo) {
         pos = select_bit(lo, j);
@@ -381,25 +379,13 @@ __device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t gam
         list = (list & ~(15u << (4 * i))) | ((uint32_t)vj << (4 * i));
     }
     e.meta = list | ((uint32_t)(P - 2) << 22);
-    // the 12 initial deals: draws 0..3 of each tier are the four words of that tier's first Philox call
+    DeckSrc src{nullptr, seed, game};
+    e.d[0] = e.d[1] = e.d[2] = 0;
 #pragma unroll 1
-    for (int t = 0; t < 3; t++) {
-        const uint4 r4 = philox(seed, game, 0, STREAM_DECK0 + t);
-        const uint32_t rr4[4] = {r4.x, r4.y, r4.z, r4.w};
-        const int size = t == 0 ? 40 : (t == 1 ? 30 : 20), base = t == 0 ? 0 : (t == 1 ? 40 : 70);
-        uint32_t lo = t == 0 ? 0xFFFFFFFFu : (t == 1 ? 0x3FFFFFFFu : 0x000FFFFFu), hi = t == 0 ? 0xFFu : 0u, w = 0;
-#pragma unroll
-        for (int d = 0; d < 4; d++) {
-            const int clo = __popc(lo), j = (int)__umulhi(rr4[d], (uint32_t)(size - d));
-            const bool in_hi = j >= clo;
-            const int pos = select_bit(in_hi ? hi : lo, in_hi ? j - clo : j);
-            lo &= ~(in_hi ? 0u : 1u << pos);
-            hi &= ~(in_hi ? 1u << pos : 0u);
-            w |= (uint32_t)(base + pos + (in_hi ? 32 : 0)) << (8 * d);
-        }
-        if (t == 0) { e.d[0] = w; e.k[0] = lo; e.k[2] = (e.k[2] & 0xF00FFFFFu) | hi << 20; }
-        else if (t == 1) { e.d[1] = w; e.k[1] = lo; }
-        else { e.d[2] = w; e.k[2] = (e.k[2] & 0xFFF00000u) | lo; }
+    for (int i = 0; i < 12; i++) {  // one copy of deal() in the binary: the reset runs once per game, the step loop 90 times
+        const int t = i >> 2;
+        const uint32_t card = deal(e, t, src) << (8 * (i & 3));
+        if (t == 0) e.d[0] |= card; else if (t == 1) e.d[1] |= card; else e.d[2] |= card;
     }
 #pragma unroll
     for (int p = 0; p < P; p++) { e.pg[p] = 0; e.pc[p] = 0; e.pr[p] = 0x00FFFFFFu; e.pi[p] = 0; }
