@@ -244,3 +244,14 @@ def test_random_tournament_statistics(oracle):
     assert m["loses"] == [N - m["wins"][i] - m["ties"][i] for i in range(2)]
     assert m["total_scores"] == (sc.astype(np.float64).sum(0) / 2).tolist()
     assert abs(sum(m["win_rates"]) + 100.0 * m["ties"][0] / N - 100.0) < 1e-9 and m["succ"]
+
+
+@pytest.mark.gpu
+def test_ppo_shaped_policy_rollout_example():
+    """examples/ppo_rollout.py on a small batch: a reference-shaped actor (265 -> 4x128 -> 3510, masked) drives the
+    vector env for two episodes' worth of steps without ever choosing an illegal action."""
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import ppo_rollout
+
+    out = ppo_rollout.rollout(num_envs=4096, steps=120, chunk=2048)
+    assert out["episodes_finished"] >= 4096 and out["env_step_calls_per_s"] > 0

@@ -198,10 +198,12 @@ def test_illegal_actions_are_flagged_and_ignored(pkg, oracle):
     assert (reward[~legal] == 0).all()
 
 
-def test_env_step_matches_oracle_emulation_of_splendor_env(pkg, oracle):
+@pytest.mark.parametrize("P", [2, 3, 4])
+def test_env_step_matches_oracle_emulation_of_splendor_env(pkg, oracle, P):
     """spl_env_step vs SplendorEnv.step semantics (splendor_env.py:127-231) emulated with the oracle: learner move,
-    Philox-random opponents until the learner's seat, then the learner's mask + observation, 100-round cap."""
-    N, P, seed = 160, 2, 31
+    Philox-random opponents (one per other seat) until the learner's seat, then the learner's mask + observation,
+    100-round cap."""
+    N, seed = (160 if P == 2 else 64), 31
     rng = np.random.default_rng(1)
     learner = rng.integers(0, P, N).astype(np.int8)
     eng = pkg.BatchedSplendor(N, P, seed=seed, first_game=0, limit_rounds=True)
@@ -217,7 +219,7 @@ def test_env_step_matches_oracle_emulation_of_splendor_env(pkg, oracle):
 
     act = np.full(N, -1, np.int16)  # reset step: opponents play up to the learner's first turn
     alive = np.ones(N, bool)
-    for it in range(120):
+    for it in range(130):
         obs, reward, term, illegal, mask = (x.cpu().numpy() for x in eng.env_step(torch.from_numpy(learner), torch.from_numpy(act)))
         for e in np.nonzero(alive)[0]:
             if act[e] >= 0:
