@@ -19,100 +19,113 @@ from .template import Agent as DummyAgent
 FREEDOM = True
 
 
+class _SeedSchedule:
+    """`random.seed(seed)` followed by 1000 per-move seeds; the global RNG is re-seeded from the list around every update
+    (twice per move), exactly the schedule of ``game.py:43-45,183,196``.  Wraps around after 500 moves."""
+
+    def __init__(self, seed):
+        random.seed(seed)
+        self.values = [random.randint(0, int(1e10)) for _ in range(1000)]
+        self.cursor = 0
+
+    def reseed(self):
+        random.seed(self.values[self.cursor % len(self.values)])
+        self.cursor += 1
+
+
 class Game:
+    """One game between `agent_list` under `GameRule`; `Run()` returns the reference's history dictionary."""
+
     def __init__(self, GameRule, agent_list, num_of_agent, seed=1, time_limit=1, warning_limit=3, displayer=None,
                  agents_namelist=("Alice", "Bob"), interactive=False):
         self.seed = seed
-        random.seed(self.seed)
-        self.seed_list = [random.randint(0, int(1e10)) for _ in range(1000)]
-        self.seed_idx = 0
-        for i, plyr in enumerate(agent_list):
-            assert plyr.id == i
-        self.game_rule = GameRule(num_of_agent)
+        self._schedule = _SeedSchedule(seed)
+        self.seed_list, self.seed_idx = self._schedule.values, 0
+        if any(agent.id != seat for seat, agent in enumerate(agent_list)):
+            raise AssertionError("agent ids must be 0..N-1 in list order")
+        self.game_rule = GameRule(num_of_agent)  # draws nobles and decks from the RNG state left by the schedule
         self.gamemaster = DummyAgent(num_of_agent)
         self.agents = agent_list
         self.agents_namelist = list(agents_namelist)
-        self.time_limit, self.warning_limit = time_limit, warning_limit
-        self.warnings = [0] * len(agent_list)
-        self.warning_positions = []
+        self.time_limit, self.warning_limit, self.interactive = time_limit, warning_limit, interactive
+        self.warnings, self.warning_positions = [0] * len(agent_list), []
         self.displayer = displayer
-        if self.displayer is not None:
-            self.displayer.InitDisplayer(self)
-        self.interactive = interactive
+        if displayer is not None:
+            displayer.InitDisplayer(self)
 
     def _EndGame(self, num_of_agent, history, isTimeOut=True, id=None):
-        history.update({"seed": self.seed, "num_of_agent": num_of_agent, "agents_namelist": self.agents_namelist,
-                        "warning_positions": self.warning_positions, "warning_limit": self.warning_limit})
-        history["scores"] = {i: 0 for i in range(num_of_agent)}
+        rule = self.game_rule
+        scores = {seat: 0 for seat in range(num_of_agent)}
         if isTimeOut:
-            history["scores"][id] = -1
+            scores[id] = -1
         else:
-            for i in range(num_of_agent):
-                history["scores"][i] = self.game_rule.calScore(self.game_rule.current_game_state, i)
+            scores = {seat: rule.calScore(rule.current_game_state, seat) for seat in range(num_of_agent)}
+        history.update(seed=self.seed, num_of_agent=num_of_agent, agents_namelist=self.agents_namelist,
+                       warning_positions=self.warning_positions, warning_limit=self.warning_limit, scores=scores)
         if self.displayer is not None:
-            self.displayer.EndGame(self.game_rule.current_game_state, history["scores"])
+            self.displayer.EndGame(rule.current_game_state, scores)
         return history
 
+    def _play_one_move(self, move_number):
+        rule = self.game_rule
+        seat = rule.getCurrentAgentIndex()
+        state = rule.current_game_state
+        state.agent_to_move = seat
+        offered = rule.getLegalActions(state, seat)
+        mover = self.agents[seat] if seat < len(self.agents) else self.gamemaster
+        if move_number == 0 and self.displayer is not None:
+            self.displayer._DisplayState(state)
+        # agents get private copies of the offer and of the state, but the live rule object (game.py:117-118,142)
+        chosen = mover.SelectAction(copy.deepcopy(offered), copy.deepcopy(state), rule)
+        self._schedule.reseed()
+        record = {move_number: {"agent_id": seat, "action": chosen}}
+        rule.update(chosen)
+        self._schedule.reseed()
+        self.seed_idx = self._schedule.cursor
+        if self.displayer is not None:
+            self.displayer.ExcuteAction(seat, chosen, rule.current_game_state)
+        return record
+
     def Run(self):
-        history = {"actions": []}
-        action_counter = 0
+        history, move_number = {"actions": []}, 0
         while not self.game_rule.gameEnds():
-            agent_index = self.game_rule.getCurrentAgentIndex()
-            agent = self.agents[agent_index] if agent_index < len(self.agents) else self.gamemaster
-            game_state = self.game_rule.current_game_state
-            game_state.agent_to_move = agent_index
-            actions = self.game_rule.getLegalActions(game_state, agent_index)
-            actions_copy, gs_copy = copy.deepcopy(actions), copy.deepcopy(game_state)
-            if action_counter == 0 and self.displayer is not None:
-                self.displayer._DisplayState(self.game_rule.current_game_state)
-            selected = agent.SelectAction(actions_copy, gs_copy, self.game_rule)
-            random.seed(self.seed_list[self.seed_idx % len(self.seed_list)])
-            self.seed_idx += 1
-            history["actions"].append({action_counter: {"agent_id": self.game_rule.current_agent_index, "action": selected}})
-            action_counter += 1
-            self.game_rule.update(selected)
-            random.seed(self.seed_list[self.seed_idx % len(self.seed_list)])
-            self.seed_idx += 1
-            if self.displayer is not None:
-                self.displayer.ExcuteAction(agent_index, selected, self.game_rule.current_game_state)
+            history["actions"].append(self._play_one_move(move_number))
+            move_number += 1
         return self._EndGame(self.game_rule.num_of_agent, history, isTimeOut=False)
 
 
 class GameReplayer:
-    """Re-applies a recorded history (``game.py:216-258``).  Because the first thing a game does with ``random`` after
-    ``random.seed(seed)`` is draw its nobles and decks, replaying under the recorded seed reproduces the same board."""
+    """Re-applies a recorded history (``game.py:216-258``).  The first thing a game does with ``random`` after seeding is
+    draw its nobles and decks, so replaying under the recorded seed reproduces the same board."""
 
     def __init__(self, GameRule, replay, displayer=None):
         self.replay = replay
         self.seed = replay["seed"]
-        random.seed(self.seed)
-        self.seed_list = [random.randint(0, int(1e10)) for _ in range(1000)]
-        self.seed_idx = 0
+        self._schedule = _SeedSchedule(self.seed)
+        self.seed_list, self.seed_idx = self._schedule.values, 0
         self.num_of_agent = replay["num_of_agent"]
         self.agents_namelist = replay["agents_namelist"]
-        self.warning_limit = replay["warning_limit"]
+        self.warning_limit, self.warning_positions = replay["warning_limit"], replay["warning_positions"]
         self.warnings = [0] * self.num_of_agent
-        self.warning_positions = replay["warning_positions"]
-        self.game_rule = GameRule(self.num_of_agent)
         self.scores = replay["scores"]
+        self.game_rule = GameRule(self.num_of_agent)
         self.displayer = displayer
-        if self.displayer is not None:
-            self.displayer.InitDisplayer(self)
+        if displayer is not None:
+            displayer.InitDisplayer(self)
 
     def Run(self):
-        for item in self.replay["actions"]:
-            ((index, info),) = item.items()
-            self.game_rule.current_agent_index = info["agent_id"]
-            random.seed(self.seed_list[self.seed_idx % len(self.seed_list)])
-            self.seed_idx += 1
-            self.game_rule.update(info["action"])
-            random.seed(self.seed_list[self.seed_idx % len(self.seed_list)])
-            self.seed_idx += 1
+        rule = self.game_rule
+        for entry in self.replay["actions"]:
+            ((_, move),) = entry.items()
+            rule.current_agent_index = move["agent_id"]
+            self._schedule.reseed()
+            rule.update(move["action"])
+            self._schedule.reseed()
             if self.displayer is not None:
-                self.displayer.ExcuteAction(info["agent_id"], info["action"], self.game_rule.current_game_state)
+                self.displayer.ExcuteAction(move["agent_id"], move["action"], rule.current_game_state)
         if self.displayer is not None:
-            self.displayer.EndGame(self.game_rule.current_game_state, self.scores)
-        return self.game_rule.current_game_state
+            self.displayer.EndGame(rule.current_game_state, self.scores)
+        return rule.current_game_state
 
 
 def tally(scores_per_game) -> dict:
