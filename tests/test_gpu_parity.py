@@ -335,3 +335,26 @@ def test_one_and_two_ply_expansion(pkg, oracle, P):
             c = kids[m].copy()
             oracle.step(c, int(legal[j]))
             assert action2[offsets2[m] + j] == legal[j] and np.array_equal(sn2[offsets2[m] + j], c.snapshot()), (m, j)
+
+
+def test_truncated_playouts_resume_to_the_same_results(pkg, oracle):
+    """max_steps cuts games short (end kind 4, states saved); continuing from the saved states with spl_playout_from gives
+    exactly the results of the uninterrupted playout - and the truncated prefix equals the oracle's."""
+    G, P, seed = 2048, 2, 21
+    full = pkg.playout_games(G, P, seed=seed, trace_len=300)
+    cut = pkg.playout_games(G, P, seed=seed, max_steps=40, trace_len=300, want_final_state=True)
+    kinds = cut["end_kind"].cpu().numpy()
+    assert (kinds[full["steps"].cpu().numpy() > 40] == 4).all() and (cut["steps"].cpu().numpy() <= 40).all()
+    c = pkg.counters_dict(cut["counters"])
+    assert c["end_truncated"] == int((kinds == 4).sum()) > 0 and c["steps"] == int(cut["steps"].to(torch.int64).sum())
+    for g in range(0, G, 64):
+        st, fin, tr, k = oracle.playout(seed, g, P, False, 40)
+        assert (int(cut["steps"][g]), int(kinds[g])) == (st, k)
+        assert np.array_equal(cut["trace"][:st, g].cpu().numpy(), tr[:st])
+    eng = pkg.BatchedSplendor(G, P, seed=seed)
+    eng.state.copy_(cut["final_state"])
+    rest = eng.playout(max_steps=1000, trace_len=300)
+    assert torch.equal(rest["score2"], full["score2"]) and torch.equal(rest["steps"], full["steps"])
+    assert torch.equal(rest["end_kind"], full["end_kind"])
+    joined = torch.where(cut["trace"] >= 0, cut["trace"], rest["trace"])
+    assert torch.equal(joined, full["trace"])
