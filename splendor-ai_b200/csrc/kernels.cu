@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -24,6 +25,7 @@ __device__ const Tables g_tables = make_tables();
 __device__ const uint32_t g_log1p_bits[32] = SPL_LOG1P_BITS;
 
 constexpr int BLOCK = 128;
+constexpr int PLAYOUT_BLOCK = 128;  // default threads per block of the playout kernel
 
 __device__ __forceinline__ void stage_tables(Tables &sT)
 {
@@ -632,10 +634,16 @@ static int launch_playout(bool fresh, const PlayoutArgs &a, int P, cudaStream_t 
     if (a.max_steps < 1 || a.max_steps > 4096 || a.trace_len < 0) return SPL_E_RANGE;
     if (a.trace && a.trace_len > 0)
         CK(cudaMemsetAsync(a.trace, 0xFF, (size_t)a.trace_len * (size_t)a.n_games * sizeof(int16_t), stream));
-    const int64_t want = (a.n_games + BLOCK - 1) / BLOCK, cap = (int64_t)sm_count() * 8;
+    static int blk = 0;
+    if (!blk) {  // SPL_PLAYOUT_BLOCK: threads per block (32, 64, 96 or 128) - a tuning knob, see profiles/r1_playout_ncu.md
+        const char *s = getenv("SPL_PLAYOUT_BLOCK");
+        blk = s ? atoi(s) : PLAYOUT_BLOCK;
+        if (blk != 32 && blk != 64 && blk != 96 && blk != 128) blk = PLAYOUT_BLOCK;
+    }
+    const int64_t want = (a.n_games + blk - 1) / blk, cap = (int64_t)sm_count() * (1024 / blk);
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    if (fresh) { DISPATCH_P(P, playout_kernel<PP, true><<<grid, BLOCK, 0, stream>>>(a)); }
-    else { DISPATCH_P(P, playout_kernel<PP, false><<<grid, BLOCK, 0, stream>>>(a)); }
+    if (fresh) { DISPATCH_P(P, playout_kernel<PP, true><<<grid, blk, 0, stream>>>(a)); }
+    else { DISPATCH_P(P, playout_kernel<PP, false><<<grid, blk, 0, stream>>>(a)); }
     CK(cudaGetLastError());
     return SPL_OK;
 }
