@@ -16,6 +16,7 @@ import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from splendor_ai_b200.env import SplendorVecEnv, unpack_mask  # noqa: E402
+from splendor_ai_b200.sampling import masked_sample  # noqa: E402
 
 
 class Actor(nn.Module):
@@ -29,13 +30,15 @@ class Actor(nn.Module):
             d = hidden
         self.body, self.head = nn.Sequential(*layers), nn.Linear(d, actions)
 
-    def forward(self, obs, mask_bits):
+    def forward(self, obs, mask_bits=None):
         logits = self.head(self.body(obs))
+        if mask_bits is None:  # raw logits: spl_masked_sample applies the bit-packed mask itself
+            return logits
         legal = unpack_mask(mask_bits, torch.bool)
         return logits.masked_fill(~legal, float("-inf"))
 
 
-def rollout(num_envs=262_144, steps=32, num_agents=2, seed=1234, chunk=65_536):
+def rollout(num_envs=262_144, steps=32, num_agents=2, seed=1234, chunk=65_536, fused_sampling=True):
     env = SplendorVecEnv(num_envs, num_agents, seed=seed)
     policy = Actor().to(env.device).eval()
     obs, info = env.reset()
@@ -45,11 +48,15 @@ def rollout(num_envs=262_144, steps=32, num_agents=2, seed=1234, chunk=65_536):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     with torch.no_grad():
-        for _ in range(steps):
+        for t in range(steps):
             actions = torch.empty(num_envs, dtype=torch.int16, device=env.device)
             for lo in range(0, num_envs, chunk):  # the dense [N, 3510] logits are produced chunk by chunk
-                logits = policy(obs[lo:lo + chunk], mask[lo:lo + chunk])
-                actions[lo:lo + chunk] = torch.distributions.Categorical(logits=logits).sample().to(torch.int16)
+                if fused_sampling:  # masked softmax + Categorical sample + log-prob in one kernel, from the mask bits
+                    a, _ = masked_sample(policy(obs[lo:lo + chunk]), mask[lo:lo + chunk], seed, t, first_id=lo)
+                    actions[lo:lo + chunk] = a
+                else:               # the plain PyTorch way: dense boolean mask, masked_fill, Categorical
+                    logits = policy(obs[lo:lo + chunk], mask[lo:lo + chunk])
+                    actions[lo:lo + chunk] = torch.distributions.Categorical(logits=logits).sample().to(torch.int16)
             obs, reward, terminated, truncated, info = env.step(actions)
             mask = info["legal_mask"]
             assert not bool(info["illegal"].any())
@@ -57,7 +64,7 @@ def rollout(num_envs=262_144, steps=32, num_agents=2, seed=1234, chunk=65_536):
             finished += terminated.sum()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return {"envs": num_envs, "steps": steps, "env_step_calls_per_s": num_envs * steps / dt, "seconds": dt,
+    return {"envs": num_envs, "steps": steps, "fused_sampling": fused_sampling, "env_step_calls_per_s": num_envs * steps / dt, "seconds": dt,
             "episodes_finished": int(finished.item()), "mean_reward_per_call": float(returns.mean().item()) / steps}
 
 
@@ -65,5 +72,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=262_144)
     ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--torch-sampling", action="store_true", help="sample with torch.distributions instead of spl_masked_sample")
     a = ap.parse_args()
-    print(json.dumps(rollout(a.envs, a.steps)))
+    print(json.dumps(rollout(a.envs, a.steps, fused_sampling=not a.torch_sampling)))

@@ -159,6 +159,15 @@ int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t firs
                  const int8_t *learner, const int16_t *action, int8_t *reward, uint8_t *terminated, uint8_t *illegal,
                  uint32_t *mask, float *obs, int64_t N, int P, uint32_t flags, void *stream);
 
+/* The rollout's action choice under the legal mask (agents/our_agents/ppo/network.py:113-115, training.py:110-116):
+ *   probs = softmax(where(mask == 0, HUGE_NEG, logits)); action ~ Categorical(probs); log_prob(action)
+ * for N rows of 3510 float32 logits (row stride in floats >= 3510) and the BIT-PACKED masks of spl_legal_mask /
+ * spl_env_step.  The sample is an inverse CDF over weights floor(exp(l - max) * 2^24) with one Philox word per row keyed
+ * (seed, row id = ids[e] or first_id + e, step, stream 6); greedy != 0 returns the arg-max (lowest index on ties) instead.
+ * log_prob (optional) = log softmax of the chosen action over the legal ones, float32 (|error| < 1e-5 vs float64). */
+int spl_masked_sample(const float *logits, int64_t row_stride, const uint32_t *mask, uint64_t seed, uint64_t first_id,
+                      const uint64_t *ids, uint32_t step, int greedy, int16_t *action, float *log_prob, int64_t N, void *stream);
+
 /* Host-buffer forms (the end-to-end path a reference-side caller uses): pageable or pinned HOST pointers in and out,
  * device staging buffers owned by the library, copies + kernel + copies on `stream`, then a stream synchronise.
  * deck_lists/nobles as in spl_inject; outputs as in spl_playout. */

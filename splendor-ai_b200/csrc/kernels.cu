@@ -455,6 +455,107 @@ __global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------- masked action sampling
+// The PPO rollout's action choice (agents/our_agents/ppo/network.py:113-115 + training.py:110-116):
+//   probs = softmax(where(mask == 0, HUGE_NEG, logits)); a ~ Categorical(probs); log_prob(a)
+// consuming the BIT-PACKED legal mask the env kernels emit.  One warp per env row: element (j, lane) = index 32*j + lane,
+// so its legality is bit `lane` of mask word j and all loads are coalesced.  The row is read once (110 values per lane
+// stay in registers).  Sampling is an exact inverse CDF over fixed-point weights floor(p * 2^24) (p = exp(l - max) in
+// (0, 1]): per-chunk totals by one warp REDUX each, a parallel prefix over the 110 totals to find the chunk, then a scan
+// inside that chunk - one Philox word per row, reproducible from (seed, row id, step).
+// Bound: HBM, 14,040 B of logits + 440 B of mask per row.
+constexpr int SAMPLE_CHUNKS = 110;
+constexpr int SAMPLE_WARPS = 4;
+
+__device__ __forceinline__ uint32_t fixed24(float p) { return (uint32_t)(p * 16777216.f); }
+
+__global__ void __launch_bounds__(32 * SAMPLE_WARPS) masked_sample_kernel(const float *logits, int64_t ld, const uint32_t *mask,
+                                                                          uint64_t seed, uint64_t first_id, const uint64_t *ids,
+                                                                          uint32_t step, int greedy, int16_t *action, float *log_prob,
+                                                                          int64_t N)
+{
+    __shared__ uint32_t chunk_total[SAMPLE_WARPS][112];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * SAMPLE_WARPS;
+    uint32_t *T = chunk_total[warp];
+    for (int64_t r = (int64_t)blockIdx.x * SAMPLE_WARPS + warp; r < N; r += nwarps) {
+        const float *L = logits + r * ld;
+        const uint32_t *M = mask + r * SPL_MASK_WORDS;
+        uint32_t mw[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) mw[q] = (q * 32 + lane < SPL_MASK_WORDS) ? M[q * 32 + lane] : 0u;
+        float v[SAMPLE_CHUNKS], mx = -INFINITY;
+        int arg = 0x7FFFFFFF;
+#pragma unroll
+        for (int j = 0; j < SAMPLE_CHUNKS; j++) {
+            const uint32_t word = __shfl_sync(0xFFFFFFFFu, mw[j >> 5], j & 31);
+            const int i = j * 32 + lane;
+            const bool legal = (word >> lane & 1u) && i < SPL_NUM_ACTIONS;
+            v[j] = legal ? L[i] : -INFINITY;
+            if (v[j] > mx) { mx = v[j]; arg = i; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {  // warp arg-max, lowest index among equal values
+            const float om = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
+            const int oa = __shfl_xor_sync(0xFFFFFFFFu, arg, o);
+            if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+        }
+        float z = 0.f;
+#pragma unroll
+        for (int j = 0; j < SAMPLE_CHUNKS; j++) {
+            v[j] = expf(v[j] - mx);  // exp(-inf) = 0 for illegal entries
+            z += v[j];
+            const uint32_t tj = __reduce_add_sync(0xFFFFFFFFu, fixed24(v[j]));
+            if (lane == 0) T[j] = tj;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xFFFFFFFFu, z, o);
+        int chosen = arg;
+        float p_chosen = 1.f;
+        if (!greedy) {
+            if (lane == 0) { T[110] = 0; T[111] = 0; }
+            __syncwarp();
+            // lane l owns chunks 4l .. 4l+3 (28 lanes cover 112 slots): prefix over lanes, then over the lane's four
+            const uint32_t t0 = lane < 28 ? T[4 * lane] : 0u, t1 = lane < 28 ? T[4 * lane + 1] : 0u,
+                           t2 = lane < 28 ? T[4 * lane + 2] : 0u, t3 = lane < 28 ? T[4 * lane + 3] : 0u;
+            unsigned long long inc = (unsigned long long)t0 + t1 + t2 + t3;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += up;
+            }
+            const unsigned long long total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            const uint64_t id = ids ? ids[r] : first_id + (uint64_t)r;
+            const uint32_t u = philox(seed, id, step, 6).x;
+            const unsigned long long target = __umul64hi(total, (unsigned long long)u << 32);  // floor(total*u/2^32) < total
+            const int owner = __ffs(__ballot_sync(0xFFFFFFFFu, inc > target)) - 1;
+            unsigned long long before = inc - ((unsigned long long)t0 + t1 + t2 + t3);  // cumulative weight before my chunks
+            int jc = 4 * lane;
+            if (before + t0 <= target) { before += t0; jc++; if (before + t1 <= target) { before += t1; jc++; if (before + t2 <= target) { before += t2; jc++; } } }
+            jc = __shfl_sync(0xFFFFFFFFu, jc, owner);
+            before = __shfl_sync(0xFFFFFFFFu, before, owner);
+#pragma unroll
+            for (int j = 0; j < SAMPLE_CHUNKS; j++) {
+                if (j != jc) continue;  // warp-uniform: exactly one chunk takes the scan
+                unsigned long long c = fixed24(v[j]);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, c, o);
+                    if (lane >= o) c += up;
+                }
+                const int src = __ffs(__ballot_sync(0xFFFFFFFFu, before + c > target)) - 1;
+                chosen = j * 32 + src;
+                p_chosen = __shfl_sync(0xFFFFFFFFu, v[j], src);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            action[r] = (int16_t)chosen;
+            if (log_prob) log_prob[r] = logf(p_chosen) - logf(z);
+        }
+    }
+}
+
 }  // namespace spl
 
 // ================================================================================================ C ABI
@@ -565,6 +666,19 @@ int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_ga
     if (N == 0) return SPL_OK;
     DISPATCH_P(P, step_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
                       (uint4 *)state, decks, seed, first_game, game_ids, action, reward, done, illegal, N, flags));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_masked_sample(const float *logits, int64_t row_stride, const uint32_t *mask, uint64_t seed, uint64_t first_id,
+                      const uint64_t *ids, uint32_t step, int greedy, int16_t *action, float *log_prob, int64_t N, void *stream)
+{
+    if (!logits || !mask || !action || N < 0 || row_stride < SPL_NUM_ACTIONS) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    const int64_t want = (N + SAMPLE_WARPS - 1) / SAMPLE_WARPS, cap = (int64_t)sm_count() * 8;
+    masked_sample_kernel<<<(unsigned)(want < cap ? want : cap), 32 * SAMPLE_WARPS, 0, (cudaStream_t)stream>>>(
+        logits, row_stride, mask, seed, first_id, ids, step, greedy, action, log_prob, N);
     CK(cudaGetLastError());
     return SPL_OK;
 }
