@@ -162,7 +162,7 @@ int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t firs
 /* The rollout's action choice under the legal mask (agents/our_agents/ppo/network.py:113-115, training.py:110-116):
  *   probs = softmax(where(mask == 0, HUGE_NEG, logits)); action ~ Categorical(probs); log_prob(action)
  * for N rows of 3510 float32 logits (row stride in floats >= 3510) and the BIT-PACKED masks of spl_legal_mask /
- * spl_env_step.  The sample is an inverse CDF over weights floor(exp(l - max) * 2^24) with one Philox word per row keyed
+ * spl_env_step.  Only the legal logits are read.  The sample is an inverse CDF over weights floor(exp(l - max) * 2^24) with one Philox word per row keyed
  * (seed, row id = ids[e] or first_id + e, step, stream 6); greedy != 0 returns the arg-max (lowest index on ties) instead.
  * log_prob (optional) = log softmax of the chosen action over the legal ones, float32 (|error| < 1e-5 vs float64). */
 int spl_masked_sample(const float *logits, int64_t row_stride, const uint32_t *mask, uint64_t seed, uint64_t first_id,

@@ -70,3 +70,19 @@ for N in a.envs:
         gbs = N * bytes_per_env / (ms * 1e-3) / 1e9
         print(json.dumps({"kernel": k, "envs": N, "players": P, "ms": ms, "envs_per_s": N / (ms * 1e-3), "bytes_per_env": bytes_per_env,
                           "GBps": gbs, "frac_of_hbm_peak": gbs / PEAK}))
+
+# masked action sampling (spl_masked_sample): 3510 float32 logits + 110 mask words per row
+from splendor_ai_b200.sampling import masked_sample  # noqa: E402
+
+for N in a.envs:
+    rows = min(N, 262144)
+    logits = torch.randn((rows, 3510), device="cuda")
+    eng = pkg.BatchedSplendor(rows, a.players, seed=1)
+    mask = eng.legal_mask()
+    ms = timed(lambda: masked_sample(logits, mask, 1, 0), a.reps)
+    n_legal = float(torch.ops.aten.bitwise_and(mask.view(torch.uint8).unsqueeze(-1) >> torch.arange(8, device="cuda", dtype=torch.uint8), 1).sum()) / rows
+    b = 440 + 32 * n_legal + 6  # mask bits + one 32-byte sector per legal logit (gather) + action/log-prob out
+    print(json.dumps({"kernel": "masked_sample", "envs": rows, "ms": ms, "rows_per_s": rows / (ms * 1e-3), "legal_per_row": n_legal,
+                      "bytes_per_env": b, "GBps": rows * b / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": rows * b / (ms * 1e-3) / 1e9 / PEAK,
+                      "dense_equivalent_GBps": rows * (3510 * 4 + 446) / (ms * 1e-3) / 1e9}))
+    break
