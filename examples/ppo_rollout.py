@@ -16,6 +16,7 @@ import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from splendor_ai_b200.env import SplendorVecEnv, unpack_mask  # noqa: E402
+from splendor_ai_b200.rollout import BatchedRolloutBuffer  # noqa: E402
 from splendor_ai_b200.sampling import masked_sample  # noqa: E402
 
 
@@ -38,11 +39,12 @@ class Actor(nn.Module):
         return logits.masked_fill(~legal, float("-inf"))
 
 
-def rollout(num_envs=262_144, steps=32, num_agents=2, seed=1234, chunk=65_536, fused_sampling=True):
+def rollout(num_envs=262_144, steps=32, num_agents=2, seed=1234, chunk=65_536, fused_sampling=True, store=False):
     env = SplendorVecEnv(num_envs, num_agents, seed=seed)
     policy = Actor().to(env.device).eval()
     obs, info = env.reset()
     mask = info["legal_mask"]
+    buffer = BatchedRolloutBuffer(steps, num_envs, device=env.device) if store else None
     finished = torch.zeros((), dtype=torch.int64, device=env.device)
     returns = torch.zeros(num_envs, device=env.device)
     torch.cuda.synchronize()
@@ -50,21 +52,28 @@ def rollout(num_envs=262_144, steps=32, num_agents=2, seed=1234, chunk=65_536, f
     with torch.no_grad():
         for t in range(steps):
             actions = torch.empty(num_envs, dtype=torch.int16, device=env.device)
+            log_probs = torch.zeros(num_envs, device=env.device)
             for lo in range(0, num_envs, chunk):  # the dense [N, 3510] logits are produced chunk by chunk
                 if fused_sampling:  # masked softmax + Categorical sample + log-prob in one kernel, from the mask bits
-                    a, _ = masked_sample(policy(obs[lo:lo + chunk]), mask[lo:lo + chunk], seed, t, first_id=lo)
-                    actions[lo:lo + chunk] = a
+                    a, lp = masked_sample(policy(obs[lo:lo + chunk]), mask[lo:lo + chunk], seed, t, first_id=lo)
+                    actions[lo:lo + chunk], log_probs[lo:lo + chunk] = a, lp
                 else:               # the plain PyTorch way: dense boolean mask, masked_fill, Categorical
                     logits = policy(obs[lo:lo + chunk], mask[lo:lo + chunk])
                     actions[lo:lo + chunk] = torch.distributions.Categorical(logits=logits).sample().to(torch.int16)
+            prev_obs, prev_mask = obs, mask
             obs, reward, terminated, truncated, info = env.step(actions)
+            if buffer is not None:  # everything stays on the device; masks stay bit-packed (440 B per decision)
+                buffer.remember(prev_obs, actions, prev_mask, log_probs, torch.zeros(num_envs, device=env.device), reward, terminated)
             mask = info["legal_mask"]
             assert not bool(info["illegal"].any())
             returns += reward
             finished += terminated.sum()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return {"envs": num_envs, "steps": steps, "fused_sampling": fused_sampling, "env_step_calls_per_s": num_envs * steps / dt, "seconds": dt,
+    if buffer is not None:
+        advantages, returns = buffer.calculate_gae(0.99)
+        assert advantages.shape == (steps, num_envs) and bool(torch.isfinite(returns).all())
+    return {"envs": num_envs, "steps": steps, "fused_sampling": fused_sampling, "stored": store, "env_step_calls_per_s": num_envs * steps / dt, "seconds": dt,
             "episodes_finished": int(finished.item()), "mean_reward_per_call": float(returns.mean().item()) / steps}
 
 
@@ -73,5 +82,6 @@ if __name__ == "__main__":
     ap.add_argument("--envs", type=int, default=262_144)
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--torch-sampling", action="store_true", help="sample with torch.distributions instead of spl_masked_sample")
+    ap.add_argument("--store", action="store_true", help="also fill a BatchedRolloutBuffer and compute returns/advantages")
     a = ap.parse_args()
-    print(json.dumps(rollout(a.envs, a.steps, fused_sampling=not a.torch_sampling)))
+    print(json.dumps(rollout(a.envs, a.steps, fused_sampling=not a.torch_sampling, store=a.store)))

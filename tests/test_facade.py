@@ -253,5 +253,5 @@ def test_ppo_shaped_policy_rollout_example():
     sys.path.insert(0, os.path.join(ROOT, "examples"))
     import ppo_rollout
 
-    out = ppo_rollout.rollout(num_envs=4096, steps=120, chunk=2048)
-    assert out["episodes_finished"] >= 4096 and out["env_step_calls_per_s"] > 0
+    out = ppo_rollout.rollout(num_envs=4096, steps=120, chunk=2048, store=True)
+    assert out["episodes_finished"] >= 4096 and out["env_step_calls_per_s"] > 0 and out["stored"]
