@@ -71,8 +71,8 @@ def rollout(num_envs=262_144, steps=32, num_agents=2, seed=1234, chunk=65_536, f
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if buffer is not None:
-        advantages, returns = buffer.calculate_gae(0.99)
-        assert advantages.shape == (steps, num_envs) and bool(torch.isfinite(returns).all())
+        advantages, norm_returns = buffer.calculate_gae(0.99)
+        assert advantages.shape == (steps, num_envs) and bool(torch.isfinite(norm_returns).all())
     return {"envs": num_envs, "steps": steps, "fused_sampling": fused_sampling, "stored": store, "env_step_calls_per_s": num_envs * steps / dt, "seconds": dt,
             "episodes_finished": int(finished.item()), "mean_reward_per_call": float(returns.mean().item()) / steps}
 
