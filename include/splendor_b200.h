@@ -53,6 +53,7 @@ extern "C" {
 
 /* rule flags */
 #define SPL_F_LIMIT_ROUNDS 1u /* LimitRoundsGameRule: also end when every agent has made 100 turns (splendor/utils.py:14-25) */
+#define SPL_F_SELF_PLAY 2u    /* spl_env_step: no in-kernel opponents; the caller's policy plays every seat (ppo.py --opponent itself) */
 
 /* end kinds written by playouts / spl_game_ends */
 #define SPL_END_NONE 0
@@ -154,7 +155,9 @@ int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t 
  * then in-kernel RandomAgent opponents until it is the learner's seat again or the game ends
  * (_simulate_opponents :219-231), then the learner's next legal mask and observation.  learner[e] = the learner's
  * seat.  action[e] < 0 = "reset step": only simulate opponents up to the learner's first turn (SplendorEnv.reset).
- * reward[e] int8, terminated[e] u8 (end kind), illegal[e] u8, mask [N][110] u32, obs [N][265] f32 (mask/obs optional). */
+ * reward[e] int8, terminated[e] u8 (end kind), illegal[e] u8, mask [N][110] u32, obs [N][265] f32 (mask/obs optional).
+ * With SPL_F_SELF_PLAY the action is applied for the seat to move (learner may be null), no opponent is simulated, and the
+ * mask / observation returned are those of the NEXT seat to move: the caller's policy plays all seats. */
 int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
                  const int8_t *learner, const int16_t *action, int8_t *reward, uint8_t *terminated, uint8_t *illegal,
                  uint32_t *mask, float *obs, int64_t N, int P, uint32_t flags, void *stream);

@@ -18,6 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 SPL_OK, SPL_E_BADARG, SPL_E_CUDA, SPL_E_NODEVICE, SPL_E_RANGE = 0, -1, -2, -3, -4
 F_LIMIT_ROUNDS = 1
+F_SELF_PLAY = 2
 END_NONE, END_SCORE, END_DEADLOCK, END_ROUNDCAP, END_TRUNCATED = range(5)
 CTR_NAMES = ("games", "steps", "wins0", "wins1", "wins2", "wins3", "ties0", "ties1", "ties2", "ties3",
              "end_score", "end_deadlock", "end_roundcap", "end_truncated", "score2_sum", "nobles")

@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, cons
     if (mask) tile_zero<ENVSTEP_TB>(tile, ENVSTEP_TB * MASK_ROW);
     if (i < N) {
         load_env(e, state, N, i);
-        me = learner[i];
+        const bool self_play = flags & SPL_F_SELF_PLAY;
+        me = self_play ? seat_of(e.meta) : (int)learner[i];
         const int a = action[i];
         const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
         int rew = 0, bad = 0;
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, cons
                 rew = apply_action(e, ch, src);
             else { bad = 1; go = false; e.meta |= META_ILLEGAL; }
         }
-        for (int guard = 0; go && guard < 4; guard++) {
+        for (int guard = 0; go && !self_play && guard < 4; guard++) {
             if (seat_of(e.meta) == me || game_ends(e, flags) != SPL_END_NONE) break;
             Ctx c;
             FamilyCounts f;
@@ -432,6 +433,7 @@ __global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, cons
         if (reward) reward[i] = (int8_t)rew;
         if (illegal) illegal[i] = (uint8_t)bad;
         if (terminated) terminated[i] = (uint8_t)game_ends(e, flags);
+        if (self_play) me = seat_of(e.meta);  // mask / observation of whoever moves next
     }
     if (mask) {  // the LEARNER's mask (get_legal_actions_mask uses my_turn, splendor_env.py:184)
         __syncthreads();
@@ -796,7 +798,7 @@ int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t firs
                  const int8_t *learner, const int16_t *action, int8_t *reward, uint8_t *terminated, uint8_t *illegal, uint32_t *mask, float *obs,
                  int64_t N, int P, uint32_t flags, void *stream)
 {
-    if (!state || !learner || !action || N < 0) return SPL_E_BADARG;
+    if (!state || (!learner && !(flags & SPL_F_SELF_PLAY)) || !action || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
     constexpr size_t smem = (size_t)ENVSTEP_TB * ENVSTEP_ROW_BYTES;

@@ -177,9 +177,12 @@ class BatchedSplendor:
                                                 _stream(self.device)), "spl_playout_from")
         return out
 
-    def env_step(self, learner: torch.Tensor, actions: torch.Tensor, want_mask: bool = True, want_obs: bool = True):
-        """SplendorEnv.step for every env: learner move, random opponents, next mask + observation (see spl_env_step)."""
-        l = learner.to(device=self.device, dtype=torch.int8).contiguous()
+    def env_step(self, learner: torch.Tensor | None, actions: torch.Tensor, want_mask: bool = True, want_obs: bool = True,
+                 self_play: bool = False):
+        """SplendorEnv.step for every env: learner move, random opponents, next mask + observation (see spl_env_step).
+        self_play=True: the action is for the seat to move, no opponents are simulated, and the mask / observation are the
+        next mover's (learner is ignored and may be None)."""
+        l = None if learner is None else learner.to(device=self.device, dtype=torch.int8).contiguous()
         a = actions.to(device=self.device, dtype=torch.int16).contiguous()
         reward = torch.empty(self.N, dtype=torch.int8, device=self.device)
         term = torch.empty(self.N, dtype=torch.uint8, device=self.device)
@@ -189,7 +192,7 @@ class BatchedSplendor:
         with torch.cuda.device(self.device):
             nat.check(self.lib.spl_env_step(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, _ptr(self.game_ids), _ptr(l), _ptr(a),
                                             _ptr(reward), _ptr(term), _ptr(illegal), _ptr(mask), _ptr(obs), self.N, self.P,
-                                            self.flags, _stream(self.device)), "spl_env_step")
+                                            self.flags | (nat.F_SELF_PLAY if self_play else 0), _stream(self.device)), "spl_env_step")
         return obs, reward, term, illegal, mask
 
     def state_numpy(self) -> np.ndarray:

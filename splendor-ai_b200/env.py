@@ -135,6 +135,9 @@ def unpack_mask(mask_words: torch.Tensor, dtype=torch.float64) -> torch.Tensor:
 class SplendorVecEnv:
     """N single-learner envs stepped by one fused kernel per call, RandomAgent opponents in-kernel, auto-reset.
 
+    self_play=True: no in-kernel opponents - every call applies the action of the seat to move (info["acted"]) and returns
+    the next mover's observation and mask (info["my_id"]), so one policy can play all seats.
+
     reset()  -> (obs [N,265] f32, {"my_id": int8 [N]})
     step(a)  -> (obs, reward f32 [N], terminated bool [N], truncated bool [N] (always False), info)
                 info: "legal_mask" [N,110] int32 bit-packed (see unpack_mask), "illegal" bool [N], "my_id"
@@ -144,7 +147,7 @@ class SplendorVecEnv:
     """
 
     def __init__(self, num_envs: int, num_agents: int = 2, seed: int = 1234, first_game: int = 0, shuffle_turns: bool = True,
-                 fixed_turn: int | None = None, device="cuda", raise_on_illegal: bool = False):
+                 fixed_turn: int | None = None, device="cuda", raise_on_illegal: bool = False, self_play: bool = False):
         self.num_envs, self.number_of_players = int(num_envs), int(num_agents)
         self.engine = BatchedSplendor(num_envs, num_agents, seed=seed, first_game=first_game, limit_rounds=True, device=device)
         self.device = self.engine.device
@@ -153,6 +156,7 @@ class SplendorVecEnv:
         self.observation_space = Box(-np.inf, np.inf, (num_envs, OBS_SIZE))
         self.single_observation_space = Box(-np.inf, np.inf, (OBS_SIZE,))
         self.shuffle_turns, self.fixed_turn, self.raise_on_illegal = shuffle_turns, fixed_turn, raise_on_illegal
+        self.self_play = self_play  # the caller's policy plays every seat (ppo.py --opponent itself); info["my_id"] = seat to move
         self._gen = torch.Generator(device="cpu").manual_seed(seed)
         self._base = first_game
         self._episode = torch.zeros(num_envs, dtype=torch.int64, device=self.device)
@@ -178,7 +182,9 @@ class SplendorVecEnv:
         self.my_turn = self._draw_seats(self.num_envs).to(self.device)
         self._done.zero_()
         skip = torch.full((self.num_envs,), -1, dtype=torch.int16, device=self.device)
-        obs, _, term, _, mask = self.engine.env_step(self.my_turn, skip)
+        obs, _, term, _, mask = self.engine.env_step(self.my_turn, skip, self_play=self.self_play)
+        if self.self_play:
+            self.my_turn = self._seat_to_move()
         self._done = term != 0
         self.legal_mask = mask
         return obs, {"my_id": self.my_turn, "legal_mask": mask}
@@ -193,14 +199,20 @@ class SplendorVecEnv:
             self.my_turn = self.my_turn.clone()
             self.my_turn[self._done] = self._draw_seats(n).to(self.device)
             a = torch.where(self._done, torch.full_like(a, -1), a)
-        obs, reward, term, illegal, mask = self.engine.env_step(self.my_turn, a)
+        obs, reward, term, illegal, mask = self.engine.env_step(self.my_turn, a, self_play=self.self_play)
+        acted = self.my_turn
+        if self.self_play:
+            self.my_turn = self._seat_to_move()
         if self.raise_on_illegal and bool(illegal.any()):
             bad = int(torch.nonzero(illegal)[0])
             raise ValueError(f"the action {int(a[bad])} is illegal! (env {bad})")
         self._done = term != 0
         self.legal_mask = mask
-        info = {"legal_mask": mask, "illegal": illegal != 0, "my_id": self.my_turn, "end_kind": term}
+        info = {"legal_mask": mask, "illegal": illegal != 0, "my_id": self.my_turn, "end_kind": term, "acted": acted}
         return obs, reward.to(torch.float32), self._done.clone(), torch.zeros_like(self._done), info
+
+    def _seat_to_move(self) -> torch.Tensor:
+        return ((self.engine.state[1, :, 3] >> 20) & 3).to(torch.int8)
 
     def get_legal_actions_mask(self, packed: bool = False, dtype=torch.float64) -> torch.Tensor:
         """The learners' current masks: bit-packed [N,110] int32, or dense [N,3510] like the reference's float64 mask."""

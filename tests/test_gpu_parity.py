@@ -358,3 +358,38 @@ def test_truncated_playouts_resume_to_the_same_results(pkg, oracle):
     assert torch.equal(rest["end_kind"], full["end_kind"])
     joined = torch.where(cut["trace"] >= 0, cut["trace"], rest["trace"])
     assert torch.equal(joined, full["trace"])
+
+
+@pytest.mark.parametrize("P", [2, 3])
+def test_self_play_env_step_matches_oracle(pkg, oracle, P):
+    """SPL_F_SELF_PLAY: the caller moves every seat; reward / end kind / next mover's mask and observation vs the oracle."""
+    from splendor_ai_b200.env import SplendorVecEnv
+
+    N, seed = 96, 17
+    env = SplendorVecEnv(N, P, seed=seed, self_play=True)
+    obs, info = env.reset()
+    orcs = [oracle.init(P, *oracle.synth_game(seed, e, P)) for e in range(N)]
+    rng = np.random.default_rng(P)
+    episode = np.zeros(N, np.int64)
+    for it in range(140):
+        o, m, who = obs.cpu().numpy(), info["legal_mask"].cpu().numpy(), info["my_id"].cpu().numpy()
+        act = np.zeros(N, np.int16)
+        for e in range(N):
+            s = orcs[e]
+            assert who[e] == s.cur
+            legal = oracle.legal(s)
+            assert np.array_equal(unpack_mask(m[e]), legal), (e, it)
+            assert np.array_equal(o[e].view(np.uint32), oracle.observe(s, s.cur).view(np.uint32)), (e, it)
+            act[e] = rng.choice(legal)
+        was_done = env._done.cpu().numpy()
+        obs, reward, term, _, info = env.step(torch.from_numpy(act))
+        reward, kind = reward.cpu().numpy(), info["end_kind"].cpu().numpy()
+        for e in range(N):
+            if was_done[e]:  # auto-reset: a fresh game, the action was ignored
+                episode[e] += 1
+                orcs[e] = oracle.init(P, *oracle.synth_game(seed, e + episode[e] * N, P))
+                assert reward[e] == 0
+            else:
+                assert reward[e] == oracle.step(orcs[e], int(act[e])), (e, it)
+            assert kind[e] == oracle.game_ends(orcs[e], True), (e, it)
+    assert (episode >= 1).mean() > 0.7  # one call = one move here, so a few long games are still running
