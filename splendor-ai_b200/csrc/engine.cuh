@@ -22,6 +22,18 @@
 #include "../../include/spl_tables.h"
 #include "../../include/splendor_b200.h"
 
+// SPL_CHECK: bounds / invariant assertions, compiled in only with -DSPL_DEBUG (compute-sanitizer is not available on
+// the GPU pool, so index safety is checked with a debug build run over tools/touch_all_kernels.py and the parity tests)
+#if defined(SPL_DEBUG) && !defined(SPL_HOSTSIM)
+#include <assert.h>
+#define SPL_CHECK(cond) assert(cond)
+#elif defined(SPL_DEBUG)
+#include <cassert>
+#define SPL_CHECK(cond) assert(cond)
+#else
+#define SPL_CHECK(cond) ((void)0)
+#endif
+
 namespace spl {
 
 constexpr uint32_t ONES6 = 0x02108421u;        // 1 in each field
@@ -335,6 +347,7 @@ __device__ __forceinline__ uint32_t deal(Env<P> &e, int tier, const DeckSrc &src
         cnt--;
         e.k[0] = set_byte(e.k[0], tier, cnt);
         const int base = tier == 0 ? 0 : (tier == 1 ? 40 : 70);
+        SPL_CHECK(cnt < (tier == 0 ? 40u : (tier == 1 ? 30u : 20u)));
         return src.lists[base + cnt];
     }
     uint32_t lo, hi = 0;
@@ -490,6 +503,7 @@ __device__ __forceinline__ int combo_len(int ci) { return ci < 5 ? 1 : (ci < 15 
 // other colours, then the combinations_with_replacement patterns (actions.py:188-199).
 __device__ __forceinline__ uint32_t diff_variant_bits(const Tables &T, const Ctx &c, int ci, int L, int ex)
 {
+    SPL_CHECK(ci >= 0 && ci < 25 && c.h1 < 64 && c.h2 < 64 && c.h3 < 64 && L == combo_len(ci));
     const uint32_t x = T.pext_diff[ci][c.h1], y = T.pext_diff[ci][c.h2], z = T.pext_diff[ci][c.h3];
     const int kk = 6 - L;
     const uint32_t two = L == 1 ? 0u : (uint32_t)(T.cwr2_pair[L == 2][x & 15u] | T.cwr2_dbl[L == 2][y & 15u]);
@@ -499,6 +513,7 @@ __device__ __forceinline__ uint32_t diff_variant_bits(const Tables &T, const Ctx
 // Same for collect_same colour `col` (actions.py:145-174): none | pairs 1..10 | one of 11..15 | two of 16..20
 __device__ __forceinline__ uint32_t same_variant_bits(const Tables &T, const Ctx &c, int col, int e2)
 {
+    SPL_CHECK(col >= 0 && col < 5 && c.h1 < 64 && c.h2 < 64);
     const uint32_t x = T.pext_same[col][c.h1], y = T.pext_same[col][c.h2];
     return e2 <= 0 ? 1u : (e2 == 1 ? x << 11 : ((uint32_t)T.pairs5[x] << 1 | y << 16));
 }
@@ -609,6 +624,7 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
                                              int total, int k, Choice &ch)
 {
     ch.C = 0; ch.R = 0; ch.info = 0; ch.slot = 0;
+    SPL_CHECK(k >= 0 && k < (total ? total : c.nS));
     if (total == 0) {  // pass (:570-574)
         ch.type = T_PASS;
         ch.n = c.S ? select_bit8(c.S, k) + 1 : 0;
@@ -679,7 +695,9 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
             ch.C = T.combo_c[ci];
         }
         const int ni = small_div(k, nv), vi = k - ni * nv;
+        SPL_CHECK(nv >= 1 && vi >= 0 && vi < __popc(vbits) && ni < c.nS);
         const int v = select_bit(vbits, vi);  // the vi-th payable return variant, ascending
+        SPL_CHECK(v < V);
         ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
         ch.R = row[v];
         ch.idx = base + ch.n * V + v;
@@ -788,8 +806,10 @@ __device__ __forceinline__ int apply_action(Env<P> &e, const Choice &ch, const D
     for (int p = 1; p < P; p++)
         if (seat == p) { g = e.pg[p]; cd = e.pc[p]; rv = e.pr[p]; pi = e.pi[p]; }
 
+    SPL_CHECK(satsub6(ch.R, g + ch.C) == 0 && satsub6(ch.C, e.bank + ch.R) == 0);  // nobody pays or takes gems that are not there
     g = g + ch.C - ch.R;
     e.bank = e.bank - ch.C + ch.R;
+    SPL_CHECK(!(g & H6) && !(e.bank & H6) && hsum6(g) <= 10);
     int score = 0;
     if (ch.type == T_RESERVE || ch.type == T_BUY_AVAILABLE) {
         const int tier = ch.slot >> 2, col = ch.slot & 3;
@@ -962,6 +982,7 @@ constexpr int OBS_ROW_BYTES = 276;  // observation staged as BYTES: 265 entries 
 __device__ __forceinline__ void or_bits64(uint32_t *m, int start, uint64_t pat)
 {
     const int w = start >> 5, sh = start & 31;
+    SPL_CHECK(start >= 0 && w + 2 < MASK_ROW);
     const uint64_t lo = pat << sh;
     m[w] |= (uint32_t)lo;
     m[w + 1] |= (uint32_t)(lo >> 32);
@@ -970,6 +991,7 @@ __device__ __forceinline__ void or_bits64(uint32_t *m, int start, uint64_t pat)
 __device__ __forceinline__ void or_bits32(uint32_t *m, int start, uint32_t pat)
 {
     const int w = start >> 5, sh = start & 31;
+    SPL_CHECK(start >= 0 && w + 1 < MASK_ROW);
     const uint64_t lo = (uint64_t)pat << sh;
     m[w] |= (uint32_t)lo;
     m[w + 1] |= (uint32_t)(lo >> 32);

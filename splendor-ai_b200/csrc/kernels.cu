@@ -328,6 +328,7 @@ template <int TB>
 __device__ __forceinline__ void tile_store(const uint32_t *tile, uint32_t *out, int n, int row_words, int row_stride)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SPL_CHECK(n >= 0 && n <= TB && row_words <= row_stride);
     for (int j = warp; j < n; j += TB / 32) {
         const uint32_t *src = tile + j * row_stride;
         uint32_t *dst = out + (int64_t)j * row_words;
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(32 * SAMPLE_WARPS) masked_sample_kernel(const 
         for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xFFFFFFFFu, z, o);
         int chosen = arg;
         float p_chosen = 1.f;
-        if (!greedy) {
+        if (!greedy && arg != 0x7FFFFFFF) {
             __syncwarp();
             // lane l sums words 4l .. 4l+3; prefix over lanes; the lane whose range holds the target resolves the word
             const uint32_t t0 = T[4 * lane], t1 = T[4 * lane + 1], t2 = T[4 * lane + 2], t3 = T[4 * lane + 3];
@@ -558,8 +559,9 @@ __global__ void __launch_bounds__(32 * SAMPLE_WARPS) masked_sample_kernel(const 
             __syncwarp();
         }
         if (lane == 0) {
-            action[r] = (int16_t)chosen;
-            if (log_prob) log_prob[r] = logf(p_chosen) - logf(z);
+            const bool none_legal = arg == 0x7FFFFFFF;  // cannot happen for Splendor masks (a pass is always legal)
+            action[r] = none_legal ? (int16_t)-1 : (int16_t)chosen;
+            if (log_prob) log_prob[r] = none_legal ? -INFINITY : logf(p_chosen) - logf(z);
         }
     }
 }

@@ -17,7 +17,7 @@ def lib():
         srcs = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_ROOT, "splendor-ai_b200", "csrc", "engine.cuh"),
                 os.path.join(_ROOT, "include", "spl_tables.h")]
         if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(map(os.path.getmtime, srcs)):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB, srcs[0]])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-DSPL_DEBUG", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB, srcs[0]])  # SPL_CHECK asserts on
         _lib = C.CDLL(_LIB)
         _lib.sim_reset.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         _lib.sim_inject.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
