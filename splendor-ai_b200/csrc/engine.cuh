@@ -484,14 +484,6 @@ __device__ __forceinline__ int n_returns(int e, const Ctx &c, uint32_t O)
 {
     return n_returns(e, __popc(c.h1 & O), __popc(c.h2 & O), __popc(c.h3 & O));
 }
-// the vi-th feasible variant in [v0, v1) of a returned-gems table row
-__device__ __forceinline__ int nth_feasible(const uint32_t *row, int v0, int v1, int vi, uint32_t gems)
-{
-    int v = v0;
-    for (; v < v1; v++)
-        if (satsub6(row[v], gems) == 0 && vi-- == 0) break;
-    return v;
-}
 __device__ __forceinline__ int reserve_variants(const Ctx &c)
 {
     return (!c.bank_yellow || c.hold < 10) ? 1 : __popc(c.h1 & NORMAL_FIELDS);
@@ -1002,14 +994,6 @@ __device__ __forceinline__ uint64_t times_nobles(uint32_t variants, int V, uint3
     const uint64_t v = variants;
     return ((slots & 1u) ? v : 0ull) | ((slots & 2u) ? v << V : 0ull) | ((slots & 4u) ? v << (2 * V) : 0ull);
 }
-// bits of the variants in [v0, v1) of a returned-gems row that the agent can actually pay
-__device__ __forceinline__ uint32_t feasible_bits(const uint32_t *row, int v0, int v1, uint32_t gems)
-{
-    uint32_t bits = 0;
-    for (int v = v0; v < v1; v++) bits |= satsub6(row[v], gems) == 0 ? 1u << v : 0u;
-    return bits;
-}
-
 // getLegalActions + create_legal_actions_mask (splendor_model.py:404-576, gym/envs/utils.py:148-164) for the seat to move,
 // OR-ed into the zeroed row m.  Noble slots: NP has bit n set for every noble slot n the action may carry.
 template <int P>
