@@ -67,7 +67,7 @@ def cpu_port_throughput(P, seconds, batch=2048, first_game=0):
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
-        return
+        return None
     P = args.players
     sample_games = 8192
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -84,7 +84,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = total_steps / dt
     sample = f"{sample_games} of the {args.games_per_gpu} games of each step ({args.steps} steps, {total_steps} env-steps, {dt:.1f} s)"
-    print(json.dumps({
+    return json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -94,7 +94,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -298,7 +298,7 @@ def run_b200(args):
     D.barrier()
     D.shutdown()
     if rank != 0:
-        return
+        return None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -331,12 +331,35 @@ def run_b200(args):
         v, cores, games, steps, dt = cpu_port_throughput(P, args.cpu_seconds)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": f"{games} of the workload's games ({steps} env-steps) in {dt:.1f} s on {cores} host threads"}
-    print(json.dumps(out))
+    return json.dumps(out)
+
+
+class _StdoutToStderr:
+    """Everything written to fd 1 while the benchmark runs (NCCL's version banner, library chatter) goes to stderr; the
+    real stdout is restored only for the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_b200(a)
+    with _StdoutToStderr() as out:
+        line = run_reference(a) if a.impl == "reference" else run_b200(a)
+        if line:
+            out.emit(line)
