@@ -963,18 +963,19 @@ __device__ __forceinline__ void final_scores(const Env<P> &e, int (&score2)[P], 
 // env; it spent ~500-800 warp-instructions per env with most lanes idle and reached only 6-7 % of HBM bandwidth
 // (profiles/r1_kernels.md), so the rule work moved to one thread and only the data movement stays cooperative.
 constexpr int MASK_ROW = 113;  // words per thread row: 110 used, odd stride (bank spread), 3 spare for or_bits' overhang
+constexpr int MASK_REGS = 112; // thread_fill_mask's private copy: every bit offset is a compile-time constant once its loops
+                               // are unrolled, so this array lives in registers and the row is written to the tile once
 constexpr int OBS_ROW_BYTES = 276;  // observation staged as BYTES: 265 entries + 4 spill bytes, 69-word (odd) row stride
 // Every observation entry is an integer in 0..255 except three, which thread_fill_obs stashes and obs_entry decodes:
 //   [1]  turns            16 bits in row[267..268]
 //   [6]  np.var numerator 16 bits in row[265..266] (5*sum(x^2) - sum(x)^2 <= 4900), divided by 25 on the way out
 //   [19..23] log(1+bp)    the table index bp in the byte, looked up on the way out
 
-// OR a bit pattern into the row at an arbitrary bit offset (row zeroed beforehand; plain read-modify-write: the row is
-// private to the thread)
+// OR a bit pattern into the thread's private mask words at a bit offset (a compile-time constant at every call site)
 __device__ __forceinline__ void or_bits64(uint32_t *m, int start, uint64_t pat)
 {
     const int w = start >> 5, sh = start & 31;
-    SPL_CHECK(start >= 0 && w + 2 < MASK_ROW);
+    SPL_CHECK(start >= 0 && w + 2 < MASK_REGS);
     const uint64_t lo = pat << sh;
     m[w] |= (uint32_t)lo;
     m[w + 1] |= (uint32_t)(lo >> 32);
@@ -983,7 +984,7 @@ __device__ __forceinline__ void or_bits64(uint32_t *m, int start, uint64_t pat)
 __device__ __forceinline__ void or_bits32(uint32_t *m, int start, uint32_t pat)
 {
     const int w = start >> 5, sh = start & 31;
-    SPL_CHECK(start >= 0 && w + 1 < MASK_ROW);
+    SPL_CHECK(start >= 0 && w + 1 < MASK_REGS);
     const uint64_t lo = (uint64_t)pat << sh;
     m[w] |= (uint32_t)lo;
     m[w + 1] |= (uint32_t)(lo >> 32);
@@ -1013,8 +1014,8 @@ __device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &
             }
         }
         const uint64_t pat = times_nobles(vr, 7, NP) | times_nobles(vr, 7, NP >> 3) << 21;
-#pragma unroll 1
-        for (uint32_t occ = c.occ; occ; occ &= occ - 1) or_bits64(m, BASE_RESERVE + 42 * (__ffs(occ) - 1), pat);
+#pragma unroll
+        for (int p = 0; p < 12; p++) or_bits64(m, BASE_RESERVE + 42 * p, (c.occ >> p & 1u) ? pat : 0ull);
         any = true;
     }
     // collect_same (:475-496) and collect_diff (:437-473): every group computes its pattern unconditionally (zero when

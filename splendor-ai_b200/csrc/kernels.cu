@@ -348,15 +348,19 @@ __global__ void __launch_bounds__(MASK_TB) legal_mask_kernel(const uint4 *state,
     uint32_t *tile = dyn_tile;  // MASK_TB x MASK_ROW words
     stage_tables(sT);
     for (int64_t base = (int64_t)blockIdx.x * MASK_TB; base < N; base += (int64_t)gridDim.x * MASK_TB) {
-        tile_zero<MASK_TB>(tile, MASK_TB * MASK_ROW);
-        __syncthreads();
         const int64_t i = base + threadIdx.x;
         if (i < N) {
             Env<P> e;
             load_env(e, state, N, i);
             Ctx c;
             make_ctx(e, sT, c);
-            thread_fill_mask(e, sT, c, tile + threadIdx.x * MASK_ROW);
+            uint32_t m[MASK_REGS];
+#pragma unroll
+            for (int w = 0; w < MASK_REGS; w++) m[w] = 0;
+            thread_fill_mask(e, sT, c, m);
+            uint32_t *row = tile + threadIdx.x * MASK_ROW;
+#pragma unroll
+            for (int w = 0; w < SPL_MASK_WORDS; w++) row[w] = m[w];
         }
         __syncthreads();
         tile_store<MASK_TB>(tile, mask + base * SPL_MASK_WORDS, (int)min((int64_t)MASK_TB, N - base), SPL_MASK_WORDS, MASK_ROW);
@@ -402,7 +406,6 @@ __global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, cons
     const int n_rows = (int)min((int64_t)ENVSTEP_TB, N - base);
     Env<P> e;
     int me = 0;
-    if (mask) tile_zero<ENVSTEP_TB>(tile, ENVSTEP_TB * MASK_ROW);
     if (i < N) {
         load_env(e, state, N, i);
         const bool self_play = flags & SPL_F_SELF_PLAY;
@@ -443,7 +446,13 @@ __global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, cons
             el.meta = (e.meta & ~(3u << 20)) | ((uint32_t)me << 20);
             Ctx c;
             make_ctx(el, sT, c);
-            thread_fill_mask(el, sT, c, tile + threadIdx.x * MASK_ROW);
+            uint32_t m[MASK_REGS];
+#pragma unroll
+            for (int w = 0; w < MASK_REGS; w++) m[w] = 0;
+            thread_fill_mask(el, sT, c, m);
+            uint32_t *row = tile + threadIdx.x * MASK_ROW;
+#pragma unroll
+            for (int w = 0; w < SPL_MASK_WORDS; w++) row[w] = m[w];
         }
         __syncthreads();
         tile_store<ENVSTEP_TB>(tile, mask + base * SPL_MASK_WORDS, n_rows, SPL_MASK_WORDS, MASK_ROW);

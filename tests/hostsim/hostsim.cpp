@@ -102,7 +102,7 @@ template <int P> static int t_mask(const uint32_t *w, int seat, uint32_t *mask)
     Env<P> e; ld(e, w);
     if (seat >= 0) e.meta = (e.meta & ~(3u << 20)) | ((uint32_t)seat << 20);
     Ctx c; make_ctx(e, T, c);
-    uint32_t m[MASK_ROW] = {0};
+    uint32_t m[MASK_REGS] = {0};
     thread_fill_mask(e, T, c, m);
     std::memcpy(mask, m, SPL_MASK_WORDS * 4);
     return 0;
