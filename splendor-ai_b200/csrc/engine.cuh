@@ -1094,9 +1094,22 @@ __device__ __forceinline__ float obs_entry(const uint8_t *row, int w, const uint
     return f;
 }
 
-// features.extract_metrics_with_cards(state, seat).astype(float32) (features.py:214-310, :377-480) into the zeroed byte row o
+// features.extract_metrics_with_cards(state, seat).astype(float32) (features.py:214-310, :377-480) into the zeroed staged
+// row o (bytes packed four to a word, assembled in registers)
+// staged observation words: OBS_ROW_BYTES / 4 registers per thread; every byte offset below is a compile-time constant
+constexpr int OBS_WORDS = OBS_ROW_BYTES / 4;
+__device__ __forceinline__ void put_byte(uint32_t *o, int idx, uint32_t v) { o[idx >> 2] |= v << (8 * (idx & 3)); }
+__device__ __forceinline__ void put_bytes64(uint32_t *o, int idx, uint64_t pat)  // up to 8 bytes starting at byte idx
+{
+    const int w = idx >> 2, sh = 8 * (idx & 3);
+    const uint64_t lo = pat << sh;
+    o[w] |= (uint32_t)lo;
+    o[w + 1] |= (uint32_t)(lo >> 32);
+    o[w + 2] |= sh ? (uint32_t)(pat >> (64 - sh)) : 0u;
+}
+
 template <int P>
-__device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T, int seat, uint8_t *o)
+__device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T, int seat, uint32_t *o)
 {
     uint32_t gems = e.pg[0], cards = e.pc[0], resv = e.pr[0], pinfo = e.pi[0];
 #pragma unroll
@@ -1110,39 +1123,36 @@ __device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T
     for (int s = 0; s < 15; s++) {
         const uint32_t w = s < 12 ? e.d[s >> 2] : resv;
         const uint32_t id = (w >> (8 * (s & 3))) & 0xFFu;
-        if (id == NONE8) continue;
-        const uint2 cw = T.card[id];
+        const bool present = id != NONE8;
+        const uint2 cw = T.card[id & 127u];  // an empty slot reads the all-zero filler and contributes nothing
         const uint32_t miss = satsub6(cw.x, bp), sum = hsum6_small(miss), sh = cw.y & 31u;
         uint32_t mx = 0;
 #pragma unroll
         for (int f = 0; f < 6; f++) mx = max(mx, field(miss, 5 * f));
         const uint32_t turns = sum == 0 ? 0u : max((sum + 2u) / 3u, mx);  // features.py:124-135
-        o[(s < 12 ? 30 : 54 - 12) + s] = (uint8_t)sum;
-        o[(s < 12 ? 42 : 57 - 12) + s] = (uint8_t)turns;
+        put_byte(o, (s < 12 ? 30 : 54 - 12) + s, sum);
+        put_byte(o, (s < 12 ? 42 : 57 - 12) + s, turns);
         {  // insert into this card's colour tuple only: select, insert, write back
             const uint32_t t = insert_sorted4(sh == 0u ? best[0] : (sh == 5u ? best[1] : (sh == 15u ? best[3] : (sh == 20u ? best[4] : best[5]))), sum);
-            best[0] = sh == 0u ? t : best[0]; best[1] = sh == 5u ? t : best[1]; best[3] = sh == 15u ? t : best[3];
-            best[4] = sh == 20u ? t : best[4]; best[5] = sh == 25u ? t : best[5];
+            best[0] = (present && sh == 0u) ? t : best[0]; best[1] = (present && sh == 5u) ? t : best[1];
+            best[3] = (present && sh == 15u) ? t : best[3]; best[4] = (present && sh == 20u) ? t : best[4];
+            best[5] = (present && sh == 25u) ? t : best[5];
         }
         // vectorize_card (features.py:377-413): one-hot over sklearn's alphabetical categories black, blue, green, red,
-        // white, yellow; the cost in alphabetical order black, blue, green, red, white; deck_id; points
-        uint8_t *v = o + 70 + 13 * s;
-        const int fld = (int)(sh / 5u);  // 0 black 1 red 3 green 4 blue 5 white
-        v[fld == 0 ? 0 : (fld == 1 ? 3 : (fld == 3 ? 2 : (fld == 4 ? 1 : 4)))] = 1;
-        v[6] = (uint8_t)field(cw.x, 0);
-        v[7] = (uint8_t)field(cw.x, 20);
-        v[8] = (uint8_t)field(cw.x, 15);
-        v[9] = (uint8_t)field(cw.x, 5);
-        v[10] = (uint8_t)field(cw.x, 25);
-        v[11] = (uint8_t)(cw.y >> 8 & 3u);
-        v[12] = (uint8_t)(cw.y >> 5 & 7u);
+        // white, yellow (bytes 0..5); the cost in alphabetical order black, blue, green, red, white (6..10); deck_id; points
+        const uint32_t fld = (sh * 13u) >> 6;                       // 0 black 1 red 3 green 4 blue 5 white
+        const uint32_t alpha = (0x412030u >> (4 * fld)) & 15u;      // -> 0 black 1 blue 2 green 3 red 4 white
+        const uint64_t head = present ? ((1ull << (8 * alpha)) | (uint64_t)field(cw.x, 0) << 48 | (uint64_t)field(cw.x, 20) << 56) : 0ull;
+        const uint64_t tail = present ? ((uint64_t)field(cw.x, 15) | (uint64_t)field(cw.x, 5) << 8 | (uint64_t)field(cw.x, 25) << 16 |
+                                         (uint64_t)(cw.y >> 8 & 3u) << 24 | (uint64_t)(cw.y >> 5 & 7u) << 32) : 0ull;
+        put_bytes64(o, 70 + 13 * s, head);      // bytes 0..7: one-hot, cost black, cost blue
+        put_bytes64(o, 70 + 13 * s + 8, tail);  // bytes 8..12: cost green, red, white, deck_id, points
     }
     // distance to each board noble (features.py:257-274)
-#pragma unroll 1
+#pragma unroll
     for (int k = 0; k < 5; k++) {
         const uint32_t id = (e.meta >> (4 * k)) & 15u;
-        if (id == 15u) continue;
-        const uint32_t missing = satsub6(T.noble[id], cards);
+        const uint32_t missing = id == 15u ? 0u : satsub6(T.noble[id], cards);
         uint32_t dist = 0;
 #pragma unroll
         for (int f = 0; f < 6; f++) {
@@ -1151,36 +1161,36 @@ __device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T
             dist += (cnt >= 1 ? t & 0xFFu : 0u) + (cnt >= 2 ? (t >> 8) & 0xFFu : 0u) + (cnt >= 3 ? (t >> 16) & 0xFFu : 0u) +
                     (cnt >= 4 ? t >> 24 : 0u);
         }
-        o[60 + k] = (uint8_t)dist;
-        o[65 + k] = (uint8_t)hsum6_small(missing);
+        put_byte(o, 60 + k, dist);
+        put_byte(o, 65 + k, hsum6_small(missing));
     }
     // the scalar metrics (features.py:284-299)
     const uint32_t score = resv >> 24;
-    o[0] = 1;
-    o[267] = (uint8_t)pinfo; o[268] = (uint8_t)(pinfo >> 8);
-    o[2] = (uint8_t)score;
-    o[3] = score >= 15u ? 1 : 0;
-    o[4] = (uint8_t)hsum6(cards);
-    o[5] = (uint8_t)__popc(~resv & 0x00808080u);
+    put_byte(o, 0, 1);
+    put_byte(o, 267, pinfo & 0xFFu); put_byte(o, 268, (pinfo >> 8) & 0xFFu);
+    put_byte(o, 2, score);
+    put_byte(o, 3, score >= 15u ? 1u : 0u);
+    put_byte(o, 4, hsum6(cards));
+    put_byte(o, 5, (uint32_t)__popc(~resv & 0x00808080u));
     int s1 = 0, s2 = 0;
 #pragma unroll
     for (int n = 0; n < 5; n++) {
         const int sh = 5 * field_of_normal(n);
         const int b = (int)field(bp, sh);
         s1 += b; s2 += b * b;
-        o[9 + n] = (uint8_t)field(cards, sh);
-        o[14 + n] = (uint8_t)b;
-        o[19 + n] = (uint8_t)b;
+        put_byte(o, 9 + n, field(cards, sh));
+        put_byte(o, 14 + n, (uint32_t)b);
+        put_byte(o, 19 + n, (uint32_t)b);
     }
-    const int var_num = 5 * s2 - s1 * s1;
-    o[265] = (uint8_t)var_num; o[266] = (uint8_t)(var_num >> 8);
-    o[7] = (uint8_t)field(gems, YSH);
-    o[8] = (uint8_t)hsum6(gems);
+    const uint32_t var_num = (uint32_t)(5 * s2 - s1 * s1);
+    put_byte(o, 265, var_num & 0xFFu); put_byte(o, 266, (var_num >> 8) & 0xFFu);
+    put_byte(o, 7, field(gems, YSH));
+    put_byte(o, 8, hsum6(gems));
 #pragma unroll
     for (int p = 0; p < P; p++) {  // features.py:276-282, its i-1 indexing quirk kept
-        const uint8_t sc = (uint8_t)(e.pr[p] >> 24);
-        if (p < seat) o[24 + p] = sc;
-        else if (p > seat) o[27 + p - 1] = sc;
+        const uint32_t sc = e.pr[p] >> 24;
+        if (p < 3) put_byte(o, 24 + p, p < seat ? sc : 0u);
+        if (p >= 1) put_byte(o, 27 + p - 1, p > seat ? sc : 0u);
     }
 }
 

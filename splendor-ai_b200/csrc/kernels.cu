@@ -375,13 +375,17 @@ __global__ void __launch_bounds__(OBS_TB) observe_kernel(const uint4 *state, con
     uint32_t *tile = dyn_tile;  // OBS_TB byte rows of OBS_ROW_BYTES
     stage_tables(sT);
     for (int64_t base = (int64_t)blockIdx.x * OBS_TB; base < N; base += (int64_t)gridDim.x * OBS_TB) {
-        tile_zero<OBS_TB>(tile, OBS_TB * OBS_ROW_BYTES / 4);
-        __syncthreads();
         const int64_t i = base + threadIdx.x;
         if (i < N) {
             Env<P> e;
             load_env(e, state, N, i);
-            thread_fill_obs(e, sT, seat ? (int)seat[i] : seat_of(e.meta), reinterpret_cast<uint8_t *>(tile) + threadIdx.x * OBS_ROW_BYTES);
+            uint32_t o[OBS_WORDS + 1];
+#pragma unroll
+            for (int w = 0; w <= OBS_WORDS; w++) o[w] = 0;
+            thread_fill_obs(e, sT, seat ? (int)seat[i] : seat_of(e.meta), o);
+            uint32_t *row = tile + threadIdx.x * OBS_WORDS;
+#pragma unroll
+            for (int w = 0; w < OBS_WORDS; w++) row[w] = o[w];
         }
         __syncthreads();
         tile_store_obs<OBS_TB>(reinterpret_cast<const uint8_t *>(tile), obs + base * SPL_OBS_SIZE, (int)min((int64_t)OBS_TB, N - base), OBS_ROW_BYTES);
@@ -459,9 +463,15 @@ __global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, cons
     }
     if (obs) {
         __syncthreads();
-        tile_zero<ENVSTEP_TB>(tile, ENVSTEP_TB * OBS_ROW_BYTES / 4);
-        __syncthreads();
-        if (i < N) thread_fill_obs(e, sT, me, reinterpret_cast<uint8_t *>(tile) + threadIdx.x * OBS_ROW_BYTES);
+        if (i < N) {
+            uint32_t o[OBS_WORDS + 1];
+#pragma unroll
+            for (int w = 0; w <= OBS_WORDS; w++) o[w] = 0;
+            thread_fill_obs(e, sT, me, o);
+            uint32_t *row = tile + threadIdx.x * OBS_WORDS;
+#pragma unroll
+            for (int w = 0; w < OBS_WORDS; w++) row[w] = o[w];
+        }
         __syncthreads();
         tile_store_obs<ENVSTEP_TB>(reinterpret_cast<const uint8_t *>(tile), obs + base * SPL_OBS_SIZE, n_rows, OBS_ROW_BYTES);
     }

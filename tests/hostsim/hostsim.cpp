@@ -133,9 +133,9 @@ template <int P> static int t_undo(uint32_t *w, int seat, int idx, int card, int
 template <int P> static int t_observe(const uint32_t *w, int seat, float *o)
 {
     Env<P> e; ld(e, w);
-    uint8_t row[OBS_ROW_BYTES] = {0};
+    uint32_t row[OBS_WORDS + 1] = {0};
     thread_fill_obs(e, T, seat, row);
-    for (int w = 0; w < SPL_OBS_SIZE; w++) o[w] = obs_entry(row, w, LOG1P);
+    for (int w = 0; w < SPL_OBS_SIZE; w++) o[w] = obs_entry(reinterpret_cast<const uint8_t *>(row), w, LOG1P);
     return 0;
 }
 template <int P> static int t_scores(const uint32_t *w, uint32_t flags, int *score2, int *outcome, int *kind)
