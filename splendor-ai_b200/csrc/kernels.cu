@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, cons
 // a parallel prefix over the 110 totals to find the word, then the owner lane walks that word's bits.  One Philox word per
 // row, keyed (seed, row id, step, stream 6).
 constexpr int SAMPLE_WARPS = 4;
+constexpr int SAMPLE_CACHE = 6;  // gathered logits parked per lane between the passes (a lane rarely owns more legal bits)
 
 __device__ __forceinline__ uint32_t fixed24(float p) { return (uint32_t)(p * 16777216.f); }
 
@@ -496,9 +497,11 @@ __global__ void __launch_bounds__(32 * SAMPLE_WARPS) masked_sample_kernel(const 
                                                                           int64_t N)
 {
     __shared__ uint32_t word_total[SAMPLE_WARPS][128];
+    __shared__ float value_cache[SAMPLE_WARPS][SAMPLE_CACHE * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nwarps = (int64_t)gridDim.x * SAMPLE_WARPS;
     uint32_t *T = word_total[warp];
+    float *cache = value_cache[warp];
     for (int64_t r = (int64_t)blockIdx.x * SAMPLE_WARPS + warp; r < N; r += nwarps) {
         const float *L = logits + r * ld;
         const uint32_t *M = mask + r * SPL_MASK_WORDS;
@@ -509,14 +512,17 @@ __global__ void __launch_bounds__(32 * SAMPLE_WARPS) masked_sample_kernel(const 
             mw[q] = w < SPL_MASK_WORDS ? M[w] : 0u;
             if (w == SPL_MASK_WORDS - 1) mw[q] &= (1u << (SPL_NUM_ACTIONS - 32 * (SPL_MASK_WORDS - 1))) - 1u;  // bits >= 3510
         }
-        // pass 1: max over the legal logits (and its index, lowest on ties)
+        // pass 1: max over the legal logits (and its index, lowest on ties); the gathered values are parked in shared
+        // memory (SAMPLE_CACHE per lane, conflict-free layout) so that the later passes do not gather again
         float mx = -INFINITY;
-        int arg = 0x7FFFFFFF;
+        int arg = 0x7FFFFFFF, n_seen = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++)
             for (uint32_t bits = mw[q]; bits; bits &= bits - 1) {
                 const int i = (q * 32 + lane) * 32 + __ffs(bits) - 1;
                 const float x = L[i];
+                if (n_seen < SAMPLE_CACHE) cache[n_seen * 32 + lane] = x;
+                n_seen++;
                 if (x > mx) { mx = x; arg = i; }  // indices ascend within a lane
             }
 #pragma unroll
@@ -527,11 +533,14 @@ __global__ void __launch_bounds__(32 * SAMPLE_WARPS) masked_sample_kernel(const 
         }
         // pass 2: partition function and per-word fixed-point totals
         float z = 0.f;
+        int n_done = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             uint32_t tot = 0;
             for (uint32_t bits = mw[q]; bits; bits &= bits - 1) {
-                const float p = expf(L[(q * 32 + lane) * 32 + __ffs(bits) - 1] - mx);
+                const float x = n_done < SAMPLE_CACHE ? cache[n_done * 32 + lane] : L[(q * 32 + lane) * 32 + __ffs(bits) - 1];
+                n_done++;
+                const float p = expf(x - mx);
                 z += p;
                 tot += fixed24(p);
             }
