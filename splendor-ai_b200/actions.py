@@ -96,7 +96,20 @@ def _count(items):
 
 
 def decode(index: int) -> Action:
-    """ALL_ACTIONS[index] without the list."""
+    """ALL_ACTIONS[index] without the list (a fresh object per call; the field values are cached)."""
+    t, collected, returned, pos, noble = _decode_fields(int(index))
+    return Action(t, None if collected is None else dict(collected), None if returned is None else dict(returned),
+                  None if pos is None else CardPosition(*pos), noble)
+
+
+@lru_cache(maxsize=None)
+def _decode_fields(index: int):
+    a = _decode_uncached(index)
+    pos = None if a.position is None else (a.position.tier, a.position.card_index, a.position.reserved_index)
+    return a.type_enum, a.collected_gems, a.returned_gems, pos, a.noble_index
+
+
+def _decode_uncached(index: int) -> Action:
     if not 0 <= index < NUM_ACTIONS:
         raise ValueError(f"The action {index} isn't a valid action")
     noble = lambda n: None if n == 0 else n - 1

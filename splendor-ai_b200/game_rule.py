@@ -18,12 +18,13 @@ cards an agent bought, the noble tuples, the action/reward trace - as presentati
 from __future__ import annotations
 
 import random
+from functools import lru_cache
 
 import numpy as np
 
 from . import actions as A
 from . import template
-from .state import NONE, TIER_BASE, TIER_SIZE, state_words, unpack
+from .state import NONE, TIER_BASE, TIER_SIZE, state_words, unpack_one
 from .tables import CARD_TABLE, NOBLE_TABLE
 
 COLOURS = {"B": "black", "r": "red", "y": "yellow", "g": "green", "b": "blue", "w": "white"}
@@ -49,6 +50,7 @@ class Card:
         return hash(self.code)
 
 
+@lru_cache(maxsize=None)
 def card_of(card_id: int) -> Card:
     colour, cost, tier, points, code = CARD_TABLE[card_id]
     return Card(_COLS[colour], code, {_COLS[c]: n for c, n in enumerate(cost) if n}, tier, points)
@@ -103,26 +105,27 @@ class SplendorState(template.GameState):
         self._refresh()
 
     def _refresh(self):
-        u = unpack(self._words.reshape(-1, 1, 4), self.num_agents)
+        u = unpack_one(self._words, self.num_agents)
         b = SplendorState.BoardState()
-        b.gems = {c: int(u["bank"][0][i]) for i, c in enumerate(_COLS)}
-        b.gems = {c: b.gems[c] for c in COLOURS.values()}
-        b.dealt = [[None if u["dealt"][0][t * 4 + j] == NONE else card_of(int(u["dealt"][0][t * 4 + j])) for j in range(4)]
-                   for t in range(3)]
-        b.nobles = [NOBLES[int(i)] for i in u["nobles"][0] if i != NONE]
-        b.decks = [[card_of(int(c)) for c in self._deck_lists[TIER_BASE[t]:TIER_BASE[t] + int(u["deck_n"][0][t])]] for t in range(3)]
+        bank = dict(zip(_COLS, u["bank"]))
+        b.gems = {c: bank[c] for c in COLOURS.values()}
+        b.dealt = [[None if u["dealt"][t * 4 + j] == NONE else card_of(u["dealt"][t * 4 + j]) for j in range(4)] for t in range(3)]
+        b.nobles = [NOBLES[i] for i in u["nobles"] if i != NONE]
+        lists = self._deck_lists
+        b.decks = [[card_of(int(c)) for c in lists[TIER_BASE[t]:TIER_BASE[t] + u["deck_n"][t]]] for t in range(3)]
         b.dealt_list = lambda: [card for deck in b.dealt for card in deck if card]
         self.board = b
         self.agents = []
         for i in range(self.num_agents):
             a = SplendorState.AgentState()
             a.id = i
-            a.score = int(u["score"][0][i])
-            a.gems = {c: int(u["gems"][0][i][_COLS.index(c)]) for c in COLOURS.values()}
+            a.score = u["score"][i]
+            held = dict(zip(_COLS, u["gems"][i]))
+            a.gems = {c: held[c] for c in COLOURS.values()}
             a.cards = {c: list(v) for c, v in self._bought[i].items()}
-            a.cards["yellow"] = [card_of(int(c)) for c in u["resv"][0][i] if c != NONE]
+            a.cards["yellow"] = [card_of(c) for c in u["resv"][i] if c != NONE]
             a.nobles = list(self._noble_tuples[i])
-            a.passed = bool(u["passed"][0][i])
+            a.passed = bool(u["passed"][i])
             a.agent_trace = self._traces[i]
             a.last_action = self._last_action[i]
             self.agents.append(a)

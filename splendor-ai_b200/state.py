@@ -160,3 +160,32 @@ def pack(fields: dict, P: int, deck_lists: np.ndarray | None = None):
         words[2 + p, :, 3] = (np.asarray(fields["turns"], np.uint32)[:, p] & 0xFFFF) | \
             (np.asarray(fields["nobles_mask"], np.uint32)[:, p] & 0x3FF) << 16 | (np.asarray(fields["passed"], np.uint32)[:, p] & 1) << 26
     return words
+
+
+def unpack_one(words, P: int) -> dict:
+    """Scalar fast path of `unpack` for ONE env given as a flat sequence of 8+4P words (plain Python ints: the
+    single-game classes decode a state after every move, and numpy on 1-element arrays is mostly overhead)."""
+    w = [int(x) for x in words]
+    g6 = lambda x: [(x >> (5 * f)) & 31 for f in FIELD_OF_COLOUR_ID]
+    b4 = lambda x: [(x >> (8 * i)) & 0xFF for i in range(4)]
+    meta = w[7]
+    explicit = bool(meta & META_EXPLICIT)
+    if explicit:
+        deck_n = b4(w[4])[:3]
+    else:
+        deck_n = [bin(w[4] | ((w[6] >> 20) & 0xFF) << 32).count("1"), bin(w[5] & 0x3FFFFFFF).count("1"), bin(w[6] & 0xFFFFF).count("1")]
+    nobles = [(meta >> (4 * k)) & 15 for k in range(5)]
+    out = dict(P=P, bank=g6(w[0]), dealt=b4(w[1]) + b4(w[2]) + b4(w[3]), nobles=[NONE if n == 15 else n for n in nobles],
+               deck_n=deck_n, explicit=explicit, cur=(meta >> 20) & 3, gems=[], cards=[], resv=[], score=[], passed=[], turns=[],
+               nobles_mask=[])
+    for p in range(P):
+        q = w[8 + 4 * p:12 + 4 * p]
+        rb = b4(q[2])
+        out["gems"].append(g6(q[0]))
+        out["cards"].append(g6(q[1])[:5])
+        out["resv"].append(rb[:3])
+        out["score"].append(rb[3])
+        out["turns"].append(q[3] & 0xFFFF)
+        out["nobles_mask"].append((q[3] >> 16) & 0x3FF)
+        out["passed"].append((q[3] >> 26) & 1)
+    return out
