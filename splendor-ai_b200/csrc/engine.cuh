@@ -546,7 +546,9 @@ __device__ __forceinline__ int diff_count(const Ctx &c, int q1, int q2, int q3, 
     return (L >= c.Lmin && L <= c.Lmax) ? n : 0;
 }
 
-template <int P>
+// COMPACT = smaller code (rolled loops) for launches where warps are spread over reset / step / finalize and the
+// instruction cache is the bottleneck (>= 2^20 games); the unrolled form is ~3 % faster for small launches.
+template <int P, bool COMPACT = false>
 __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, const Ctx &c, FamilyCounts &f)
 {
     f.res = c.n_resv < 3 ? __popc(c.occ) * c.nS * reserve_variants(c) : 0;
@@ -572,7 +574,7 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
     const uint32_t eff = (c.gems & ~(31u << YSH)) + c.cards;    // gems + bought cards per colour (<= 14)
     const uint32_t cap = ((c.cards + 9u * ONES6) & H6) | (16u << YSH);  // guard bit set where 7 cards of the colour are owned (+ filler)
     uint32_t lo = 0, hi = 0;
-#ifndef SPL_ROLL_BUY  // unrolled: 3 % faster at 65,536 games per launch; rolled: 2 % faster at 2^20 (smaller code)
+    if (!COMPACT) {
 #pragma unroll
     for (int s = 0; s < 15; s++) {
         const uint32_t w = s < 12 ? e.d[s >> 2] : c.resv;
@@ -583,7 +585,7 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
         const uint32_t cnt = ok ? (uint32_t)max(__popc(c.S | ((c.near >> sh) & 31u)), 1) : 0u;
         if (s < 8) lo |= cnt << (4 * s); else hi |= cnt << (4 * (s - 8));
     }
-#else
+    } else {
     // four groups of four slots (three board rows, then the reserved list whose 4th byte is forced empty): rolled to keep
     // the step loop inside the instruction cache (profiles/r1h: no_instruction stalls when warps are spread over
     // reset / step / finalize code)
@@ -603,7 +605,7 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
         lo |= g < 2 ? gw : 0u;
         hi |= g < 2 ? 0u : gw;
     }
-#endif
+    }
     f.buy_lo = lo; f.buy_hi = hi;
     f.bav = (int)(nibble_sum(lo) + nibble_sum(hi & 0xFFFFu));
     f.bres = (int)nibble_sum(hi >> 16);

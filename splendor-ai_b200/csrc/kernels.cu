@@ -114,7 +114,7 @@ __device__ __forceinline__ uint32_t turns_total(const Env<P> &e)
     return t;
 }
 
-template <int P, bool FRESH>
+template <int P, bool FRESH, bool COMPACT>
 __global__ void __launch_bounds__(BLOCK) playout_kernel(const PlayoutArgs a)
 {
     __shared__ Tables sT;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(BLOCK) playout_kernel(const PlayoutArgs a)
                 Choice ch;
                 const uint32_t r = philox_inline(a.seed, src.game, (uint32_t)t, STREAM_ACTION).x;
                 make_ctx(e, sT, c);
-                const int total = count_legal(e, sT, c, f);
+                const int total = count_legal<P, COMPACT>(e, sT, c, f);
                 select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
                 if (a.trace && t < a.trace_len) a.trace[(int64_t)t * a.n_games + g] = (int16_t)ch.idx;
                 apply_action(e, ch, src);
@@ -794,8 +794,14 @@ static int launch_playout(bool fresh, const PlayoutArgs &a, int P, cudaStream_t 
     }
     const int64_t want = (a.n_games + blk - 1) / blk, cap = (int64_t)sm_count() * (1024 / blk);
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    if (fresh) { DISPATCH_P(P, playout_kernel<PP, true><<<grid, blk, 0, stream>>>(a)); }
-    else { DISPATCH_P(P, playout_kernel<PP, false><<<grid, blk, 0, stream>>>(a)); }
+    // large sweeps (every lane plays many games, warps drift apart) run the size-optimised instantiation
+    static int force = -1;
+    if (force < 0) { const char *s = getenv("SPL_PLAYOUT_COMPACT"); force = s ? (atoi(s) ? 1 : 0) : 2; }
+    const bool compact = force == 2 ? a.n_games >= 4 * (int64_t)grid * blk : force == 1;
+    if (fresh && compact) { DISPATCH_P(P, playout_kernel<PP, true, true><<<grid, blk, 0, stream>>>(a)); }
+    else if (fresh) { DISPATCH_P(P, playout_kernel<PP, true, false><<<grid, blk, 0, stream>>>(a)); }
+    else if (compact) { DISPATCH_P(P, playout_kernel<PP, false, true><<<grid, blk, 0, stream>>>(a)); }
+    else { DISPATCH_P(P, playout_kernel<PP, false, false><<<grid, blk, 0, stream>>>(a)); }
     CK(cudaGetLastError());
     return SPL_OK;
 }
