@@ -95,7 +95,8 @@ int spl_reset(void *state, uint64_t seed, uint64_t first_game, const uint64_t *g
 int spl_inject(void *state, const uint8_t *deck_lists, const uint8_t *nobles, int64_t N, int P, void *stream);
 
 /* SplendorGameRule.getLegalActions(state, seat to move) as a 3510-bit mask: mask[e*110 + i/32] bit i%32
- * (splendor_model.py:404-576 + gym/envs/utils.py:148-164 create_legal_actions_mask).  Warp-per-env kernel. */
+ * (splendor_model.py:404-576 + gym/envs/utils.py:148-164 create_legal_actions_mask).  One thread builds a row in registers,
+ * the block stores the rows coalesced. */
 int spl_legal_mask(const void *state, uint32_t *mask, int64_t N, int P, void *stream);
 
 /* GameRule.update(action) = generateSuccessor + seat advance (splendor_model.py:222-295, template.py:47-53) for one

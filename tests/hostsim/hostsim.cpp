@@ -23,7 +23,6 @@ static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((ui
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __uint_as_float(uint32_t b) { float f; std::memcpy(&f, &b, 4); return f; }
-static inline uint32_t atomicOr(uint32_t *p, uint32_t v) { uint32_t o = *p; *p |= v; return o; }
 using std::max;
 using std::min;
 

@@ -30,7 +30,7 @@ def _check_decision(sim, orc, oracle, where):
     want = oracle.legal(orc)
     assert np.array_equal(sim.legal_select(), want), (where, "count/select")
     assert np.array_equal(sim.legal_member(), want), (where, "membership")
-    assert np.array_equal(S.mask_to_indices(sim.mask()), want), (where, "mask lanes")
+    assert np.array_equal(S.mask_to_indices(sim.mask()), want), (where, "mask row")
     assert np.array_equal(sim.mask(), oracle.legal_mask(orc)), where
     for seat in range(sim.P):
         a, b = sim.observe(seat), oracle.observe(orc, seat)
