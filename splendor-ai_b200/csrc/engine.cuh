@@ -1,11 +1,13 @@
 // engine.cuh -- device-side Splendor rules for sm_100a: packed state words, SWAR helpers, legal-action
-// count / select / membership, action application, terminal test and scoring.
+// count / select / membership, action application and its inverse, terminal test and scoring, and the per-thread
+// builders of one legal-mask row and one observation row.
 //
 // Rule semantics follow the reference (paths relative to /root/reference/src/splendor/):
 //   getLegalActions      splendor/splendor_model.py:404-576   generate_return_combos :329-367
 //   resources_sufficient splendor/splendor_model.py:371-394   noble_visit            :397-402
 //   generateSuccessor    splendor/splendor_model.py:222-295   GameRule.update template.py:47-53
 //   gameEnds / calScore  splendor/splendor_model.py:299-323   LimitRoundsGameRule splendor/utils.py:14-25
+//   generatePredecessor splendor/splendor_model.py:156-220  features          splendor/features.py:470-480
 //   ALL_ACTIONS order    splendor/gym/envs/actions.py:109-237
 // but the formulation is different on purpose: the reference materialises a list of dicts; here every count is a
 // closed form over a handful of 32-bit words, so that one thread can play one game entirely out of registers.

@@ -29,7 +29,7 @@ def test_fuzzed_states_legal_sets_observations_and_successors(oracle, seed):
         want = oracle.legal(orc)
         assert np.array_equal(sim.legal_select(), want), (seed, it, "count/select")
         assert np.array_equal(sim.legal_member(), want), (seed, it, "membership")
-        assert np.array_equal(sim.mask(), oracle.legal_mask(orc)), (seed, it, "mask lanes")
+        assert np.array_equal(sim.mask(), oracle.legal_mask(orc)), (seed, it, "mask row")
         for seat in range(P):
             assert np.array_equal(sim.observe(seat).view(np.uint32), oracle.observe(orc, seat).view(np.uint32)), (seed, it, seat)
         for flags in (0, 1):
