@@ -962,13 +962,12 @@ __device__ __forceinline__ void final_scores(const Env<P> &e, int (&score2)[P], 
 }
 
 // ------------------------------------------------------------------------------------------------ mask + observation
-// The legal-action MASK (3510 bits) and the OBSERVATION (265 floats) are built by ONE THREAD PER ENV into its own row of
-// a shared-memory tile, which the block then stores to HBM coalesced (kernels.cu).  A first version used one warp per
-// env; it spent ~500-800 warp-instructions per env with most lanes idle and reached only 6-7 % of HBM bandwidth
-// (profiles/r1_kernels.md), so the rule work moved to one thread and only the data movement stays cooperative.
-constexpr int MASK_ROW = 113;  // words per thread row: 110 used, odd stride (bank spread), 3 spare for or_bits' overhang
-constexpr int MASK_REGS = 112; // thread_fill_mask's private copy: every bit offset is a compile-time constant once its loops
-                               // are unrolled, so this array lives in registers and the row is written to the tile once
+// The legal-action MASK (3510 bits) and the OBSERVATION (265 floats) are built by ONE THREAD PER ENV, in registers, and
+// handed to the kernel as a finished row (kernels.cu stages the rows in shared memory and moves them to HBM in bulk).
+// A first version used one warp per env; it spent ~500-800 warp-instructions per env with most lanes idle and reached only
+// 6-7 % of HBM bandwidth (profiles/r1_kernels.md), so the rule work moved to one thread and only the data movement is shared.
+constexpr int MASK_REGS = 112; // thread_fill_mask's row: 110 words + 2 spare for or_bits' overhang; every bit offset is a
+                               // compile-time constant once its loops are unrolled, so the array lives in registers
 constexpr int OBS_ROW_BYTES = 276;  // observation staged as BYTES: 265 entries + 4 spill bytes, 69-word (odd) row stride
 // Every observation entry is an integer in 0..255 except three, which thread_fill_obs stashes and obs_entry decodes:
 //   [1]  turns            16 bits in row[267..268]
@@ -1001,8 +1000,11 @@ __device__ __forceinline__ uint64_t times_nobles(uint32_t variants, int V, uint3
 }
 // getLegalActions + create_legal_actions_mask (splendor_model.py:404-576, gym/envs/utils.py:148-164) for the seat to move,
 // OR-ed into the zeroed row m.  Noble slots: NP has bit n set for every noble slot n the action may carry.
-template <int P>
-__device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &T, const Ctx &c, uint32_t *m)
+// `done(w0, w1)` is called as soon as words [w0, w1) (even bounds) are final, in ascending order and covering 0..110 with
+// [0, 2) last: a kernel stores them right away, so only a quarter of the row is ever live in registers.
+struct MaskKeep { __device__ __forceinline__ void operator()(int, int) const {} };
+template <int P, class Done = MaskKeep>
+__device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &T, const Ctx &c, uint32_t *m, Done done = Done())
 {
     const uint32_t NP = c.S ? c.S << 1 : 1u;
     bool any = false;
@@ -1036,6 +1038,7 @@ __device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &
             any_bits |= vs;
         }
     }
+    done(2, 34);  // reserve and collect_same end at bit 1139
 #pragma unroll
     for (int ci = 0; ci < 25; ci++) {
         const int L = ci < 5 ? 1 : (ci < 15 ? 2 : 3), V = L == 1 ? 6 : (L == 2 ? 15 : 20);
@@ -1049,6 +1052,8 @@ __device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &
             if (np_hi) or_bits64(m, base + 3 * V, times_nobles(vd, V, np_hi));
         }
         any_bits |= vd;
+        if (ci == 14) done(34, 68);  // lengths 1 and 2 end at bit 2219
+        if (ci == 19) done(68, 88);  // five of the ten triples: bit 2819
     }
     any = any || any_bits;
     // buy (:522-568): 6 noble bits per card; board slots 0-4 / 5-9 / 10-11 and the reserved cards as four 32-bit patterns
@@ -1075,7 +1080,9 @@ __device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &
         or_bits32(m, BASE_BUY_RESERVE, br);
         any = any || (b0 | b1 | b2 | br);
     }
+    done(88, 110);
     if (!any) m[0] |= NP;  // pass, only when nothing else is legal (:570-574)
+    done(0, 2);
 }
 
 // insert d into the ascending 4-tuple held in the bytes of t (keeps the four smallest)
@@ -1112,8 +1119,9 @@ __device__ __forceinline__ void put_bytes64(uint32_t *o, int idx, uint64_t pat) 
     o[w + 2] |= sh ? (uint32_t)(pat >> (64 - sh)) : 0u;
 }
 
-template <int P>
-__device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T, int seat, uint32_t *o)
+// `done(w0, w1)` is called when words [w0, w1) are final: the card vectors as each card is finished, the metrics last
+template <int P, class Done = MaskKeep>
+__device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T, int seat, uint32_t *o, Done done = Done())
 {
     uint32_t gems = e.pg[0], cards = e.pc[0], resv = e.pr[0], pinfo = e.pi[0];
 #pragma unroll
@@ -1151,6 +1159,7 @@ __device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T
                                          (uint64_t)(cw.y >> 8 & 3u) << 24 | (uint64_t)(cw.y >> 5 & 7u) << 32) : 0ull;
         put_bytes64(o, 70 + 13 * s, head);      // bytes 0..7: one-hot, cost black, cost blue
         put_bytes64(o, 70 + 13 * s + 8, tail);  // bytes 8..12: cost green, red, white, deck_id, points
+        done(s == 0 ? 18 : (70 + 13 * s) >> 2, (70 + 13 * (s + 1)) >> 2);  // later cards start at byte 70 + 13 (s + 1)
     }
     // distance to each board noble (features.py:257-274)
 #pragma unroll
@@ -1196,6 +1205,8 @@ __device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T
         if (p < 3) put_byte(o, 24 + p, p < seat ? sc : 0u);
         if (p >= 1) put_byte(o, 27 + p - 1, p > seat ? sc : 0u);
     }
+    done(0, 18);
+    done((70 + 13 * 15) >> 2, OBS_WORDS);
 }
 
 }  // namespace spl

@@ -3,12 +3,14 @@
 //   playout_kernel      thread-per-game, state in registers for the whole game: reset -> {terminal test, legal count,
 //                       Philox choice, k-th legal action, apply} x steps -> calScore -> counters.  No HBM traffic inside
 //                       the loop except the optional trace.
-//   legal_mask_kernel   thread-per-env rule work into a shared-memory tile (one 3510-bit row per thread, built from 32/64-bit
-//                       group patterns), then the block streams the tile to HBM coalesced.
+//   legal_mask_kernel   persistent; one thread builds one env's 3510-bit row in registers (32/64-bit group patterns) and
+//                       flushes finished words into its warp's dense shared-memory tile; lane 0 sends the warp's 32 rows
+//                       (14,080 contiguous bytes) to HBM with one bulk copy (cp.async.bulk) while the warp moves on.
 //   step_kernel         thread-per-env: decode the ALL_ACTIONS index, membership test, apply, reward / done / illegal.
-//   observe_kernel      same tile scheme for the 265-float observation.
-//   env_step_kernel     the PPO rollout call: learner move + in-kernel random opponents + the learner's next mask and
-//                       observation, one thread per env, state read and written once.
+//   observe_kernel      same scheme for the 265-float observation: rows staged as bytes, widened to float32 on the way
+//                       out with coalesced stores, warp by warp (no block barrier).
+//   env_move_kernel     the PPO rollout call's first part: learner move + in-kernel random opponents, thread-per-env at
+//                       full occupancy; spl_env_step then runs observe_kernel and legal_mask_kernel for the learner's seat.
 //   reset / inject / final_scores: thread-per-env.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -300,181 +302,177 @@ __global__ void __launch_bounds__(BLOCK) final_scores_kernel(const uint4 *state,
 }
 
 // ---------------------------------------------------------------------------------------------- tiles
-// mask / observation kernels: one thread computes one env's row into a shared-memory tile (engine.cuh thread_fill_*),
-// then the block streams the tile to HBM with fully coalesced 32-bit stores (rows are contiguous in the output).
+// mask / observation kernels: one thread computes one env's row into a shared-memory tile (engine.cuh thread_fill_*).
+// Mask rows are DENSE in the tile (440 B apart), so the 32 rows of a warp are one contiguous, 16-byte aligned 14,080-byte
+// span of the output: lane 0 hands it to the bulk-copy engine (cp.async.bulk shared -> global, SASS UBLKCP) and the warp
+// moves on - no store loop, no block barrier.  Observation rows are staged as bytes and widened to float32 on the way out
+// by the block (coalesced 32-bit stores).
 extern __shared__ __align__(16) uint32_t dyn_tile[];
 
-template <int TB>
-__device__ __forceinline__ void tile_zero(uint32_t *tile, int words)
+__device__ __forceinline__ void bulk_store_async(void *gdst, const void *ssrc, uint32_t bytes)
 {
-    uint4 *t4 = reinterpret_cast<uint4 *>(tile);
-    for (int i = threadIdx.x; i < words / 4; i += TB) t4[i] = make_uint4(0, 0, 0, 0);
-    for (int i = (words & ~3) + threadIdx.x; i < words; i += TB) tile[i] = 0;
+    SPL_CHECK((bytes & 15u) == 0 && ((uintptr_t)gdst & 15u) == 0);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
 }
-// staged byte rows -> float32 observations, coalesced
-template <int TB>
-__device__ __forceinline__ void tile_store_obs(const uint8_t *tile, float *out, int n, int row_stride_bytes)
+// the issuing thread: all its bulk stores have finished READING shared memory (the tile may be overwritten)
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// make this thread's st.shared visible to the bulk-copy engine (async proxy); follow with the warp / block sync
+__device__ __forceinline__ void fence_smem_to_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int MASK_ROW_BYTES = SPL_MASK_WORDS * 4;
+static_assert((32 * MASK_ROW_BYTES) % 16 == 0 && MASK_ROW_BYTES % 8 == 0, "a warp's mask rows must be a 16-byte multiple");
+
+// one thread's finished mask words [w0, w1) -> its dense tile row (64-bit stores: rows are 8-byte aligned; a half-warp's
+// 16 rows start 14 banks apart, so the 32 banks are hit once each)
+struct MaskRowSink {
+    uint2 *row;
+    const uint32_t *m;
+    __device__ __forceinline__ void operator()(int w0, int w1) const
+    {
+#pragma unroll
+        for (int w = w0; w < w1; w += 2) row[w >> 1] = make_uint2(m[w], m[w + 1]);
+    }
+};
+// rows [0, n) of a warp's tile -> out; all 32 lanes call it after their rows are written
+__device__ __forceinline__ void mask_tile_store(const uint32_t *wtile, uint32_t *out, int n, int lane)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int j = warp; j < n; j += TB / 32) {
-        const uint8_t *row = tile + j * row_stride_bytes;
+    fence_smem_to_async_proxy();
+    __syncwarp();
+    if ((n & 1) == 0) {  // n * 440 is a multiple of 16
+        if (lane == 0 && n > 0) bulk_store_async(out, wtile, (uint32_t)n * MASK_ROW_BYTES);
+    } else {             // ragged last tile with an odd row count: plain coalesced stores
+        for (int w = lane; w < n * SPL_MASK_WORDS; w += 32) out[w] = wtile[w];
+    }
+}
+
+// a warp's staged byte rows [0, n) -> float32 observations: lane l writes entries l, l + 32, ... of each row (coalesced
+// 128-byte stores); bytes widen to float with the 2^23 trick (one OR, one FADD, exact below 2^23)
+__device__ __forceinline__ float byte_to_float(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
+__device__ __forceinline__ void obs_tile_store(const uint8_t *wtile, float *out, int n, int lane)
+{
+    constexpr int FULL = SPL_OBS_SIZE / 32;  // 8 full 32-entry groups, then 9 entries
+#pragma unroll 2
+    for (int j = 0; j < n; j++) {
+        const uint8_t *row = wtile + j * OBS_ROW_BYTES;
         float *dst = out + (int64_t)j * SPL_OBS_SIZE;
         dst[lane] = obs_entry(row, lane, g_log1p_bits);  // the three special entries (turns, variance, log table) are all < 32
-        for (int w = lane + 32; w < SPL_OBS_SIZE; w += 32) dst[w] = (float)row[w];
+#pragma unroll
+        for (int k = 1; k < FULL; k++) dst[lane + 32 * k] = byte_to_float(row[lane + 32 * k]);
+        if (lane < SPL_OBS_SIZE - 32 * FULL) dst[lane + 32 * FULL] = byte_to_float(row[lane + 32 * FULL]);
     }
 }
-// rows [0, n) of `row_words` used words (row stride `row_stride` in the tile) -> out[0 .. n*row_words)
-template <int TB>
-__device__ __forceinline__ void tile_store(const uint32_t *tile, uint32_t *out, int n, int row_words, int row_stride)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SPL_CHECK(n >= 0 && n <= TB && row_words <= row_stride);
-    for (int j = warp; j < n; j += TB / 32) {
-        const uint32_t *src = tile + j * row_stride;
-        uint32_t *dst = out + (int64_t)j * row_words;
-        for (int w = lane; w < row_words; w += 32) dst[w] = src[w];
+struct ObsRowSink {
+    uint32_t *row;
+    const uint32_t *o;
+    __device__ __forceinline__ void operator()(int w0, int w1) const
+    {
+#pragma unroll
+        for (int w = w0; w < w1; w++) row[w] = o[w];
     }
-}
+};
 
-constexpr int MASK_TB = 64;
+constexpr int MASK_TB = 224;     // default block sizes (warps work independently in the mask kernel; the tile caps residency)
 constexpr int OBS_TB = 128;
-constexpr int ENVSTEP_TB = 64;
-constexpr int ENVSTEP_ROW_BYTES = MASK_ROW * 4 > OBS_ROW_BYTES ? MASK_ROW * 4 : OBS_ROW_BYTES;
+constexpr int TILE_TB_MAX = 512; // SPL_MASK_BLOCK / SPL_OBS_BLOCK may raise the block size up to this
 
 template <int P>
-__global__ void __launch_bounds__(MASK_TB) legal_mask_kernel(const uint4 *state, uint32_t *mask, int64_t N)
+__global__ void __launch_bounds__(TILE_TB_MAX) legal_mask_kernel(const uint4 *state, const int8_t *seat, uint32_t *mask, int64_t N)
 {
     __shared__ Tables sT;
-    uint32_t *tile = dyn_tile;  // MASK_TB x MASK_ROW words
     stage_tables(sT);
-    for (int64_t base = (int64_t)blockIdx.x * MASK_TB; base < N; base += (int64_t)gridDim.x * MASK_TB) {
-        const int64_t i = base + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *wtile = dyn_tile + warp * (32 * SPL_MASK_WORDS);  // this warp's 32 dense rows
+    for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32; base < N; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + lane;
+        if (lane == 0) bulk_store_wait_read();  // the previous tile has left shared memory
+        __syncwarp();
         if (i < N) {
             Env<P> e;
             load_env(e, state, N, i);
+            if (seat) e.meta = (e.meta & ~(3u << 20)) | ((uint32_t)seat[i] << 20);  // the mask of this seat, whoever is to move
             Ctx c;
             make_ctx(e, sT, c);
             uint32_t m[MASK_REGS];
 #pragma unroll
             for (int w = 0; w < MASK_REGS; w++) m[w] = 0;
-            thread_fill_mask(e, sT, c, m);
-            uint32_t *row = tile + threadIdx.x * MASK_ROW;
-#pragma unroll
-            for (int w = 0; w < SPL_MASK_WORDS; w++) row[w] = m[w];
+            thread_fill_mask(e, sT, c, m, MaskRowSink{reinterpret_cast<uint2 *>(wtile + lane * SPL_MASK_WORDS), m});
         }
-        __syncthreads();
-        tile_store<MASK_TB>(tile, mask + base * SPL_MASK_WORDS, (int)min((int64_t)MASK_TB, N - base), SPL_MASK_WORDS, MASK_ROW);
-        __syncthreads();
+        mask_tile_store(wtile, mask + base * SPL_MASK_WORDS, (int)min((int64_t)32, N - base), lane);
     }
+    if (lane == 0) bulk_store_wait_read();
 }
 
 template <int P>
-__global__ void __launch_bounds__(OBS_TB) observe_kernel(const uint4 *state, const int8_t *seat, float *obs, int64_t N)
+__global__ void __launch_bounds__(TILE_TB_MAX) observe_kernel(const uint4 *state, const int8_t *seat, float *obs, int64_t N)
 {
     __shared__ Tables sT;
-    uint32_t *tile = dyn_tile;  // OBS_TB byte rows of OBS_ROW_BYTES
     stage_tables(sT);
-    for (int64_t base = (int64_t)blockIdx.x * OBS_TB; base < N; base += (int64_t)gridDim.x * OBS_TB) {
-        const int64_t i = base + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *wtile = dyn_tile + warp * (32 * OBS_WORDS);  // this warp's 32 byte rows
+    for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32; base < N; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + lane;
         if (i < N) {
             Env<P> e;
             load_env(e, state, N, i);
             uint32_t o[OBS_WORDS + 1];
 #pragma unroll
             for (int w = 0; w <= OBS_WORDS; w++) o[w] = 0;
-            thread_fill_obs(e, sT, seat ? (int)seat[i] : seat_of(e.meta), o);
-            uint32_t *row = tile + threadIdx.x * OBS_WORDS;
-#pragma unroll
-            for (int w = 0; w < OBS_WORDS; w++) row[w] = o[w];
+            thread_fill_obs(e, sT, seat ? (int)seat[i] : seat_of(e.meta), o, ObsRowSink{wtile + lane * OBS_WORDS, o});
         }
-        __syncthreads();
-        tile_store_obs<OBS_TB>(reinterpret_cast<const uint8_t *>(tile), obs + base * SPL_OBS_SIZE, (int)min((int64_t)OBS_TB, N - base), OBS_ROW_BYTES);
-        __syncthreads();
+        __syncwarp();
+        obs_tile_store(reinterpret_cast<const uint8_t *>(wtile), obs + base * SPL_OBS_SIZE, (int)min((int64_t)32, N - base), lane);
+        __syncwarp();
     }
 }
 
 // ---------------------------------------------------------------------------------------------- PPO env step
-// One thread per env, everything out of registers: the learner's action (membership-checked), RandomAgent opponents until
-// the learner's seat or the end (_simulate_opponents, splendor_env.py:219-231), then the learner's next legal mask and
-// observation built into the block's tile and stored coalesced.  The state is read and written exactly once.
+// The learner's action (membership-checked), then RandomAgent opponents until the learner's seat or the end
+// (_simulate_opponents, splendor_env.py:219-231): one thread per env out of registers, at full occupancy.  The learner's
+// next observation and legal mask come from observe_kernel / legal_mask_kernel on the same stream: a fused version of the
+// three was slower (0.214 ms against 0.16 ms per 262,144 envs) because the shared-memory tile of the row kernels caps
+// residency at 14 warps per SM, and this latency-bound part then runs at that occupancy too.
 template <int P>
-__global__ void __launch_bounds__(ENVSTEP_TB) env_step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
-                                                              const uint64_t *game_ids, const int8_t *learner, const int16_t *action,
-                                                              int8_t *reward, uint8_t *terminated, uint8_t *illegal, uint32_t *mask,
-                                                              float *obs, int64_t N, uint32_t flags)
+__global__ void __launch_bounds__(BLOCK) env_move_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+                                                         const uint64_t *game_ids, const int8_t *learner, const int16_t *action,
+                                                         int8_t *reward, uint8_t *terminated, uint8_t *illegal, int64_t N, uint32_t flags)
 {
     __shared__ Tables sT;
-    uint32_t *tile = dyn_tile;  // ENVSTEP_TB rows of ENVSTEP_ROW_BYTES: the mask rows first, then the observation byte rows
     stage_tables(sT);
-    const int64_t base = (int64_t)blockIdx.x * ENVSTEP_TB, i = base + threadIdx.x;
-    const int n_rows = (int)min((int64_t)ENVSTEP_TB, N - base);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
     Env<P> e;
-    int me = 0;
-    if (i < N) {
-        load_env(e, state, N, i);
-        const bool self_play = flags & SPL_F_SELF_PLAY;
-        me = self_play ? seat_of(e.meta) : (int)learner[i];
-        const int a = action[i];
-        const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
-        int rew = 0, bad = 0;
-        bool go = true;
-        if (a >= 0) {
-            Ctx c;
-            Choice ch;
-            make_ctx(e, sT, c);
-            if (seat_of(e.meta) == me && game_ends(e, flags) == SPL_END_NONE && decode_and_check(e, sT, c, a, ch))
-                rew = apply_action(e, ch, src);
-            else { bad = 1; go = false; e.meta |= META_ILLEGAL; }
-        }
-        for (int guard = 0; go && !self_play && guard < 4; guard++) {
-            if (seat_of(e.meta) == me || game_ends(e, flags) != SPL_END_NONE) break;
-            Ctx c;
-            FamilyCounts f;
-            Choice ch;
-            const uint32_t r = philox(seed, src.game, turns_total(e), STREAM_ACTION).x;
-            make_ctx(e, sT, c);
-            const int total = count_legal(e, sT, c, f);
-            select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
-            apply_action(e, ch, src);
-        }
-        store_env(e, state, N, i);
-        if (reward) reward[i] = (int8_t)rew;
-        if (illegal) illegal[i] = (uint8_t)bad;
-        if (terminated) terminated[i] = (uint8_t)game_ends(e, flags);
-        if (self_play) me = seat_of(e.meta);  // mask / observation of whoever moves next
+    load_env(e, state, N, i);
+    const bool self_play = flags & SPL_F_SELF_PLAY;
+    const int me = self_play ? seat_of(e.meta) : (int)learner[i];
+    const int a = action[i];
+    const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
+    int rew = 0, bad = 0;
+    bool go = true;
+    if (a >= 0) {
+        Ctx c;
+        Choice ch;
+        make_ctx(e, sT, c);
+        if (seat_of(e.meta) == me && game_ends(e, flags) == SPL_END_NONE && decode_and_check(e, sT, c, a, ch))
+            rew = apply_action(e, ch, src);
+        else { bad = 1; go = false; e.meta |= META_ILLEGAL; }
     }
-    if (mask) {  // the LEARNER's mask (get_legal_actions_mask uses my_turn, splendor_env.py:184)
-        __syncthreads();
-        if (i < N) {
-            Env<P> el = e;
-            el.meta = (e.meta & ~(3u << 20)) | ((uint32_t)me << 20);
-            Ctx c;
-            make_ctx(el, sT, c);
-            uint32_t m[MASK_REGS];
-#pragma unroll
-            for (int w = 0; w < MASK_REGS; w++) m[w] = 0;
-            thread_fill_mask(el, sT, c, m);
-            uint32_t *row = tile + threadIdx.x * MASK_ROW;
-#pragma unroll
-            for (int w = 0; w < SPL_MASK_WORDS; w++) row[w] = m[w];
-        }
-        __syncthreads();
-        tile_store<ENVSTEP_TB>(tile, mask + base * SPL_MASK_WORDS, n_rows, SPL_MASK_WORDS, MASK_ROW);
+    for (int guard = 0; go && !self_play && guard < 4; guard++) {
+        if (seat_of(e.meta) == me || game_ends(e, flags) != SPL_END_NONE) break;
+        Ctx c;
+        FamilyCounts f;
+        Choice ch;
+        const uint32_t r = philox(seed, src.game, turns_total(e), STREAM_ACTION).x;
+        make_ctx(e, sT, c);
+        const int total = count_legal(e, sT, c, f);
+        select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
+        apply_action(e, ch, src);
     }
-    if (obs) {
-        __syncthreads();
-        if (i < N) {
-            uint32_t o[OBS_WORDS + 1];
-#pragma unroll
-            for (int w = 0; w <= OBS_WORDS; w++) o[w] = 0;
-            thread_fill_obs(e, sT, me, o);
-            uint32_t *row = tile + threadIdx.x * OBS_WORDS;
-#pragma unroll
-            for (int w = 0; w < OBS_WORDS; w++) row[w] = o[w];
-        }
-        __syncthreads();
-        tile_store_obs<ENVSTEP_TB>(reinterpret_cast<const uint8_t *>(tile), obs + base * SPL_OBS_SIZE, n_rows, OBS_ROW_BYTES);
-    }
+    store_env(e, state, N, i);
+    if (reward) reward[i] = (int8_t)rew;
+    if (illegal) illegal[i] = (uint8_t)bad;
+    if (terminated) terminated[i] = (uint8_t)game_ends(e, flags);
 }
 
 // ---------------------------------------------------------------------------------------------- masked action sampling
@@ -628,6 +626,25 @@ static int sm_count()
     return sms;
 }
 
+// tile kernels: block size (a multiple of 32, overridable for experiments), dynamic shared memory above 48 KB, residency
+static int tile_block(const char *env_name, int dflt)
+{
+    const char *v = getenv(env_name);
+    const int tb = v ? atoi(v) : dflt;
+    return (tb >= 32 && tb <= TILE_TB_MAX && tb % 32 == 0) ? tb : dflt;
+}
+template <class K>
+static cudaError_t allow_smem(K kernel, size_t dyn_bytes)
+{
+    return dyn_bytes + sizeof(Tables) > 48 * 1024 ? cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes)
+                                                  : cudaSuccess;
+}
+static int resident_blocks(size_t dyn_bytes)  // per SM, by shared memory (227 KB usable, 1 KB reserved per block)
+{
+    const int n = (int)((227 * 1024) / (dyn_bytes + sizeof(Tables) + 1024));
+    return n < 1 ? 1 : n;
+}
+
 #define DISPATCH_P(P, ...)             \
     switch (P) {                       \
     case 2: { constexpr int PP = 2; __VA_ARGS__; } break; \
@@ -683,17 +700,36 @@ int spl_inject(void *state, const uint8_t *deck_lists, const uint8_t *nobles, in
     return SPL_OK;
 }
 
+// persistent row kernels: as many blocks as the tile lets reside, each warp strides over 32-env groups
+static int launch_mask(const void *state, const int8_t *seat, uint32_t *mask, int64_t N, int P, cudaStream_t stream)
+{
+    static const int tb = tile_block("SPL_MASK_BLOCK", MASK_TB);
+    const size_t smem = (size_t)tb * MASK_ROW_BYTES;
+    const int64_t want = (N + tb - 1) / tb, cap = (int64_t)sm_count() * resident_blocks(smem);
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    DISPATCH_P(P, CK(allow_smem(legal_mask_kernel<PP>, smem));
+               legal_mask_kernel<PP><<<grid, tb, smem, stream>>>((const uint4 *)state, seat, mask, N));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+static int launch_observe(const void *state, const int8_t *seat, float *obs, int64_t N, int P, cudaStream_t stream)
+{
+    static const int tb = tile_block("SPL_OBS_BLOCK", OBS_TB);
+    const size_t smem = (size_t)tb * OBS_ROW_BYTES;
+    const int64_t want = (N + tb - 1) / tb, cap = (int64_t)sm_count() * resident_blocks(smem);
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    DISPATCH_P(P, CK(allow_smem(observe_kernel<PP>, smem));
+               observe_kernel<PP><<<grid, tb, smem, stream>>>((const uint4 *)state, seat, obs, N));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
 int spl_legal_mask(const void *state, uint32_t *mask, int64_t N, int P, void *stream)
 {
     if (!state || !mask || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    constexpr size_t smem = (size_t)MASK_TB * MASK_ROW * 4;
-    const int64_t want = (N + MASK_TB - 1) / MASK_TB, cap = (int64_t)sm_count() * 6;
-    const unsigned grid = (unsigned)(want < cap ? want : cap);
-    DISPATCH_P(P, legal_mask_kernel<PP><<<grid, MASK_TB, smem, (cudaStream_t)stream>>>((const uint4 *)state, mask, N));
-    CK(cudaGetLastError());
-    return SPL_OK;
+    return launch_mask(state, nullptr, mask, N, P, (cudaStream_t)stream);
 }
 
 int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids, const int16_t *action,
@@ -773,12 +809,7 @@ int spl_observe(const void *state, const int8_t *seat, float *obs, int64_t N, in
     if (!state || !obs || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    constexpr size_t smem = (size_t)OBS_TB * OBS_ROW_BYTES;
-    const int64_t want = (N + OBS_TB - 1) / OBS_TB, cap = (int64_t)sm_count() * 6;
-    const unsigned grid = (unsigned)(want < cap ? want : cap);
-    DISPATCH_P(P, observe_kernel<PP><<<grid, OBS_TB, smem, (cudaStream_t)stream>>>((const uint4 *)state, seat, obs, N));
-    CK(cudaGetLastError());
-    return SPL_OK;
+    return launch_observe(state, seat, obs, N, P, (cudaStream_t)stream);
 }
 
 static int launch_playout(bool fresh, const PlayoutArgs &a, int P, cudaStream_t stream)
@@ -837,10 +868,14 @@ int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t firs
     if (!state || (!learner && !(flags & SPL_F_SELF_PLAY)) || !action || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    constexpr size_t smem = (size_t)ENVSTEP_TB * ENVSTEP_ROW_BYTES;
-    DISPATCH_P(P, env_step_kernel<PP><<<grid_for(N, ENVSTEP_TB), ENVSTEP_TB, smem, (cudaStream_t)stream>>>(
-                      (uint4 *)state, decks, seed, first_game, game_ids, learner, action, reward, terminated, illegal, mask, obs, N, flags));
+    const int8_t *seat = (flags & SPL_F_SELF_PLAY) ? nullptr : learner;  // self-play: whoever moves next
+    DISPATCH_P(P, env_move_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
+                      (uint4 *)state, decks, seed, first_game, game_ids, learner, action, reward, terminated, illegal, N, flags));
     CK(cudaGetLastError());
+    if (obs)
+        if (int rc = launch_observe(state, seat, obs, N, P, (cudaStream_t)stream)) return rc;
+    if (mask)  // the LEARNER's mask (get_legal_actions_mask uses my_turn, splendor_env.py:184)
+        if (int rc = launch_mask(state, seat, mask, N, P, (cudaStream_t)stream)) return rc;
     return SPL_OK;
 }
 
