@@ -120,6 +120,22 @@ int spl_expand(const void *state, const uint8_t *decks, uint64_t seed, uint64_t 
                const int64_t *offsets, void *out_state, int16_t *out_action, int8_t *out_reward, int32_t *out_parent, int64_t N,
                int64_t M, int P, void *stream);
 
+/* MiniMaxAgent (agents/our_agents/minmax.py), the reference's depth-2 search agent and the default PPO test opponent
+ * (arguments_parsing.py:107), for 2-player envs.
+ * spl_minimax_eval: _evaluation_function(state) (:90-136) from seat[e]'s point of view (null = the seat to move), float64,
+ *   bit-exact with the reference (same operation order).  Any P.
+ * spl_minimax2: SelectAction (:32-88) for the seat to move of every env.  offsets[0..N] are the exclusive prefix sums of
+ *   spl_count_legal (offsets[N] = M).  child_value[offsets[e]+j] = the depth-2 value of env e's j-th legal action (ascending
+ *   ALL_ACTIONS order) = min over the opponent's replies of the evaluation; child_action = its index.  best_action /
+ *   best_value (optional): the maximum; exact ties resolve to the lowest type rank in the reference's sort (buy_available,
+ *   buy_reserve, collect_diff, collect_same, pass, reserve), then the lowest index - the reference's own order inside a
+ *   type is a random.shuffle.  Like the reference, no terminal test between the plies; replacement cards come from the
+ *   env's deck (the search peeks at it, as generateSuccessor does).  P must be 2. */
+int spl_minimax_eval(const void *state, const int8_t *seat, double *value, int64_t N, int P, void *stream);
+int spl_minimax2(const void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
+                 const int64_t *offsets, double *child_value /*[M]*/, int16_t *child_action /*[M]*/, int16_t *best_action /*[N]*/,
+                 double *best_value /*[N]*/, int64_t N, int64_t M, int P, void *stream);
+
 /* SplendorGameRule.generatePredecessor(state, action, agent_id) (splendor_model.py:156-220): undo one action per env for
  * seat[e].  Besides the ALL_ACTIONS index the undo needs what the reference reads from the action dict: card[e] = id of
  * the card that was bought / reserved (0xFF otherwise), noble[e] = id of the noble that was claimed (0xFF if none),

@@ -108,6 +108,8 @@ def lib():
         L.orc_undo.restype = C.c_int
         L.orc_describe_action.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), u8p, u8p]
         L.orc_describe_action.restype = C.c_int
+        L.orc_minimax_eval.argtypes = [sp, C.c_int]; L.orc_minimax_eval.restype = C.c_double
+        L.orc_minimax2.argtypes = [sp, u16p, C.POINTER(C.c_double)]; L.orc_minimax2.restype = C.c_int
         _lib = L
     return _lib
 
@@ -201,3 +203,16 @@ def describe_action(idx: int):
 def undo(s: State, seat: int, idx: int, card: int, noble: int, returned) -> int:
     r = np.ascontiguousarray(returned, np.uint8)
     return lib().orc_undo(C.byref(s), seat, int(idx), int(card), int(noble), _ptr(r, C.c_uint8))
+
+
+def minimax_eval(s: State, me: int) -> float:
+    """MiniMaxAgent._evaluation_function (minmax.py:90-136) for agent `me`, float64."""
+    return float(lib().orc_minimax_eval(C.byref(s), me))
+
+
+def minimax2(s: State):
+    """Depth-2 minimax values of every legal action of the seat to move: (actions uint16 [n], values float64 [n])."""
+    acts = np.zeros(1024, np.uint16)
+    vals = np.zeros(1024, np.float64)
+    n = lib().orc_minimax2(C.byref(s), _ptr(acts, C.c_uint16), _ptr(vals, C.c_double))
+    return acts[:n].copy(), vals[:n].copy()

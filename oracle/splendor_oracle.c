@@ -11,6 +11,7 @@
  *   ALL_ACTIONS index        splendor/gym/envs/actions.py:109-237, gym/envs/utils.py:148-181
  *   observation vector       splendor/features.py:214-310, :377-480
  *   RandomAgent              agents/generic/random.py:21-27
+ *   MiniMaxAgent             agents/our_agents/minmax.py:32-136 (float64 evaluation, depth-2 search)
  *
  * PARITY PIN: the reference ships no tests or golden vectors.  This oracle is pinned against
  * the reference itself, executed in the build container: oracle/gen_golden.py drives the unmodified Python engine
@@ -787,4 +788,79 @@ int orc_undo(orc_state *s, int seat, int idx, int card, int noble, const uint8_t
     a->score = (uint8_t)(a->score + score);
     a->passed = (A.type == T_PASS);
     return 0;
+}
+
+/* ------------------------------------------------------------------ MiniMaxAgent (agents/our_agents/minmax.py) */
+static const uint16_t COST_ORDER[SPL_NUM_CARDS] = SPL_CARD_COST_ORDER;
+
+/* _evaluation_function (:90-136) from agent `me`'s point of view.  float64 with the reference's operation order:
+ * Python evaluates a * b * c left to right, `reward -= x` one term at a time over board cards (tier-major, slots in
+ * order) then the agent's reserved cards, each card's cost.items() in dict order; np.var(list(gems.values())) =
+ * mean of squared deviations from sum/6 over black, red, yellow, green, blue, white.  Build with -ffp-contract=off. */
+double orc_minimax_eval(const orc_state *s, int me)
+{
+    const orc_player *a = &s->pl[me];
+    int max_score = 0;
+    for (int i = 0; i < s->P; i++) if (s->pl[i].score > max_score) max_score = s->pl[i].score;
+    if (max_score >= 15) {
+        double r = (double)(99999 + max_score);
+        return max_score > a->score ? -r : r;
+    }
+    int gem_sum = 0;
+    for (int c = 0; c < 6; c++) gem_sum += a->gems[c];
+    const double gems_factor = gem_sum >= 8 ? -0.7 : 0.1;
+    double x[6], mean = 0.0, ss = 0.0;
+    for (int k = 0; k < 6; k++) { x[k] = (double)a->gems[ALLG[k]]; mean += x[k]; }
+    mean = mean / 6.0;
+    for (int k = 0; k < 6; k++) { double d = x[k] - mean; ss += d * d; }
+    const double gems_var = ss / 6.0;
+
+    double reward = 0.0;
+    for (int slot = 0; slot < 12 + a->n_resv; slot++) {
+        const int id = slot < 12 ? s->dealt[slot] : a->resv[slot - 12];
+        if (id == NONE) continue;
+        const int col = CARD[id].colour;
+        int relevant = 0;
+        for (int k = 0; k < s->n_nobles; k++) {
+            const uint8_t *nc = NOBLE_COST[s->nobles[k]];
+            if (nc[col] > 0 && a->cards[col] < nc[col]) relevant++;
+        }
+        const double weight = (double)(CARD[id].points + 1) + (double)relevant * 0.5;
+        for (unsigned o = COST_ORDER[id]; (o & 7u) != 7u; o >>= 3) {
+            const int c = (int)(o & 7u);
+            const int diff = (int)CARD[id].cost[c] - ((int)a->gems[c] + (int)a->cards[c]);
+            double t = (double)diff * 0.1;
+            t = t * weight;
+            reward = reward - (t < 0 ? -t : t);
+        }
+    }
+    double r = reward + (double)(a->score * 2);
+    r = r + 6.0 * 0.7; /* len(agent_state.cards) is the number of colour keys: always 6 */
+    r = r + (double)gem_sum * gems_factor;
+    r = r + gems_var * -0.2;
+    return r;
+}
+
+/* _select_action_recursion (:43-88) at DEPTH 2 for the seat to move, without the alpha-beta cut (same root values for
+ * the chosen action): values[i] = min over the opponent's replies of the evaluation, for root action
+ * actions[i] (ascending ALL_ACTIONS order).  No terminal test between plies, as in the reference.  Returns the count. */
+int orc_minimax2(const orc_state *s, uint16_t *actions, double *values)
+{
+    const int me = s->cur;
+    const int n = orc_legal(s, me, actions);
+    for (int i = 0; i < n; i++) {
+        orc_state c1 = *s;
+        orc_step(&c1, actions[i]);
+        uint16_t reply[1024];
+        const int m = orc_legal(&c1, c1.cur, reply);
+        double best = 1.0 / 0.0;
+        for (int j = 0; j < m; j++) {
+            orc_state c2 = c1;
+            orc_step(&c2, reply[j]);
+            const double v = orc_minimax_eval(&c2, me);
+            if (v < best) best = v;
+        }
+        values[i] = best;
+    }
+    return n;
 }

@@ -25,7 +25,8 @@ CTR_NAMES = ("games", "steps", "wins0", "wins1", "wins2", "wins3", "ties0", "tie
 
 EXPORTS = ("spl_abi_version", "spl_state_words", "spl_last_cuda_error", "spl_error_string", "spl_warmup", "spl_reset",
            "spl_inject", "spl_legal_mask", "spl_step", "spl_final_scores", "spl_observe", "spl_playout", "spl_playout_from",
-           "spl_env_step", "spl_playout_host", "spl_undo", "spl_count_legal", "spl_expand", "spl_masked_sample")
+           "spl_env_step", "spl_playout_host", "spl_undo", "spl_count_legal", "spl_expand", "spl_masked_sample",
+           "spl_minimax_eval", "spl_minimax2")
 
 
 class SplendorNativeError(RuntimeError):
@@ -40,7 +41,7 @@ def _nvcc() -> str:
 
 
 def _sources():
-    return [os.path.join(CSRC, "kernels.cu"), os.path.join(CSRC, "engine.cuh"),
+    return [os.path.join(CSRC, "kernels.cu"), os.path.join(CSRC, "engine.cuh"), os.path.join(CSRC, "minimax.cuh"),
             os.path.join(INCLUDE, "spl_tables.h"), os.path.join(INCLUDE, "splendor_b200.h")]
 
 
@@ -78,6 +79,8 @@ def lib():
         L.spl_step.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, i64, i32, u32, vp]
         L.spl_count_legal.argtypes = [vp, vp, i64, i32, vp]
         L.spl_expand.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, i64, i64, i32, vp]
+        L.spl_minimax_eval.argtypes = [vp, vp, vp, i64, i32, vp]
+        L.spl_minimax2.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, i64, i64, i32, vp]
         L.spl_masked_sample.argtypes = [vp, i64, vp, u64, u64, vp, u32, i32, vp, vp, i64, vp]
         L.spl_undo.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp]
         L.spl_final_scores.argtypes = [vp, vp, vp, vp, i64, i32, u32, vp]

@@ -20,6 +20,7 @@
 #include <mutex>
 
 #include "engine.cuh"
+#include "minimax.cuh"
 
 namespace spl {
 
@@ -281,6 +282,85 @@ __global__ void __launch_bounds__(BLOCK) expand_kernel(const uint4 *state, const
         if (out_reward) out_reward[base + k] = (int8_t)rew;
         if (out_parent) out_parent[base + k] = (int32_t)i;
     }
+}
+
+// ---------------------------------------------------------------------------------------------- depth-2 minimax
+// MiniMaxAgent (agents/our_agents/minmax.py): one thread per ROOT ACTION.  Thread c finds its root env in the prefix sums,
+// re-derives the root's c-th legal action, plays it, then walks every reply of the opponent (k-th legal action, apply on a
+// register copy, evaluate) keeping the minimum - the grandchildren never exist in memory.  No terminal test between the
+// plies and no alpha-beta cut: the cut changes neither the root value nor the action chosen (a cut child returns a bound
+// <= the best so far and the root only replaces on a strict improvement).
+__global__ void __launch_bounds__(BLOCK) minimax_children_kernel(const uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+                                                                 const uint64_t *game_ids, const int64_t *offsets, double *child_value,
+                                                                 int16_t *child_action, int64_t N, int64_t M)
+{
+    __shared__ Tables sT;
+    stage_tables(sT);
+    const int64_t cidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cidx >= M) return;
+    int64_t lo = 0, hi = N;  // the root env: largest i with offsets[i] <= cidx
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= cidx) lo = mid; else hi = mid;
+    }
+    const int64_t i = lo;
+    Env<2> e;
+    load_env(e, state, N, i);
+    const int me = seat_of(e.meta);
+    const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
+    Choice ch;
+    {
+        Ctx c;
+        FamilyCounts f;
+        make_ctx(e, sT, c);
+        const int total = count_legal(e, sT, c, f);
+        select_legal(e, sT, c, f, total, (int)(cidx - offsets[i]), ch);
+        apply_action(e, ch, src);
+    }
+    Ctx c;
+    FamilyCounts f;
+    make_ctx(e, sT, c);
+    const int total = count_legal(e, sT, c, f), n = total ? total : c.nS;
+    double best = __longlong_as_double(0x7FF0000000000000LL);
+    for (int k = 0; k < n; k++) {
+        Choice reply;
+        select_legal(e, sT, c, f, total, k, reply);
+        Env<2> g = e;
+        apply_action(g, reply, src);
+        best = fmin(best, minimax_eval(g, sT, me));
+    }
+    child_value[cidx] = best;
+    if (child_action) child_action[cidx] = (int16_t)ch.idx;
+}
+
+// per root: the maximum child value; among exactly equal maxima the reference takes the first in its (type name, shuffle)
+// order - here the lowest type rank, then the lowest ALL_ACTIONS index
+__global__ void __launch_bounds__(BLOCK) minimax_root_kernel(const int64_t *offsets, const double *child_value, const int16_t *child_action,
+                                                             int16_t *best_action, double *best_value, int64_t N)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double bv = -__longlong_as_double(0x7FF0000000000000LL);
+    int ba = -1, br = 99;
+    for (int64_t k = offsets[i]; k < offsets[i + 1]; k++) {
+        const double v = child_value[k];
+        const int a = child_action[k], r = minimax_type_rank(a);
+        if (v > bv || (v == bv && r < br)) { bv = v; ba = a; br = r; }
+    }
+    if (best_action) best_action[i] = (int16_t)ba;
+    if (best_value) best_value[i] = bv;
+}
+
+template <int P>
+__global__ void __launch_bounds__(BLOCK) minimax_eval_kernel(const uint4 *state, const int8_t *seat, double *value, int64_t N)
+{
+    __shared__ Tables sT;
+    stage_tables(sT);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Env<P> e;
+    load_env(e, state, N, i);
+    value[i] = minimax_eval(e, sT, seat ? (int)seat[i] : seat_of(e.meta));
 }
 
 template <int P>
@@ -778,6 +858,34 @@ int spl_expand(const void *state, const uint8_t *decks, uint64_t seed, uint64_t 
                       (const uint4 *)state, decks, seed, first_game, game_ids, offsets, (uint4 *)out_state, out_action, out_reward,
                       out_parent, N, M));
     CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_minimax_eval(const void *state, const int8_t *seat, double *value, int64_t N, int P, void *stream)
+{
+    if (!state || !value || N < 0) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    DISPATCH_P(P, minimax_eval_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>((const uint4 *)state, seat, value, N));
+    CK(cudaGetLastError());
+    return SPL_OK;
+}
+
+int spl_minimax2(const void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
+                 const int64_t *offsets, double *child_value, int16_t *child_action, int16_t *best_action, double *best_value,
+                 int64_t N, int64_t M, int P, void *stream)
+{
+    if (!state || !offsets || !child_value || !child_action || N < 0 || M < 0) return SPL_E_BADARG;
+    if (P != 2) return SPL_E_BADARG;  // the reference agent asserts a 2-player game (minmax.py:16,38)
+    if (int rc = check_device()) return rc;
+    if (N == 0 || M == 0) return SPL_OK;
+    minimax_children_kernel<<<grid_for(M, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>((const uint4 *)state, decks, seed, first_game, game_ids,
+                                                                                 offsets, child_value, child_action, N, M);
+    CK(cudaGetLastError());
+    if (best_action || best_value) {
+        minimax_root_kernel<<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(offsets, child_value, child_action, best_action, best_value, N);
+        CK(cudaGetLastError());
+    }
     return SPL_OK;
 }
 

@@ -134,6 +134,32 @@ class BatchedSplendor:
         child.game_ids = base_ids[idx].contiguous()
         return child, action, reward, parent, offsets
 
+    def minimax_eval(self, seat: torch.Tensor | None = None) -> torch.Tensor:
+        """MiniMaxAgent._evaluation_function (minmax.py:90-136) per env as float64 [N]; seat int8 per env (None = seat to move)."""
+        out = torch.empty(self.N, dtype=torch.float64, device=self.device)
+        s = None if seat is None else seat.to(device=self.device, dtype=torch.int8).contiguous()
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_minimax_eval(_ptr(self.state), _ptr(s), _ptr(out), self.N, self.P, _stream(self.device)), "spl_minimax_eval")
+        return out
+
+    def minimax2(self):
+        """MiniMaxAgent.SelectAction (minmax.py:32-88, depth 2) for the seat to move of every 2-player env.  Returns
+        (best_action int16 [N], best_value float64 [N], child_action int16 [M], child_value float64 [M], offsets int64 [N+1]):
+        the children of env e are entries offsets[e] .. offsets[e+1]-1, one per legal action in ascending index order."""
+        counts = self.count_legal()
+        offsets = torch.zeros(self.N + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(counts, 0, out=offsets[1:])
+        M = int(offsets[-1].item())
+        child_value = torch.empty(M, dtype=torch.float64, device=self.device)
+        child_action = torch.empty(M, dtype=torch.int16, device=self.device)
+        best_action = torch.empty(self.N, dtype=torch.int16, device=self.device)
+        best_value = torch.empty(self.N, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.spl_minimax2(_ptr(self.state), _ptr(self.decks), self.seed, self.first_game, _ptr(self.game_ids), _ptr(offsets),
+                                            _ptr(child_value), _ptr(child_action), _ptr(best_action), _ptr(best_value), self.N, M, self.P,
+                                            _stream(self.device)), "spl_minimax2")
+        return best_action, best_value, child_action, child_value, offsets
+
     def undo(self, seat: torch.Tensor, actions: torch.Tensor, card: torch.Tensor, noble: torch.Tensor, returned: torch.Tensor):
         """generatePredecessor for one action per env (see spl_undo): seat int8, action int16 (<0 = skip), card / noble
         uint8 ids (255 = none), returned uint8 [N,6] by colour id."""

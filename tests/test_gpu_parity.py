@@ -198,6 +198,37 @@ def test_illegal_actions_are_flagged_and_ignored(pkg, oracle):
     assert (reward[~legal] == 0).all()
 
 
+@pytest.mark.parametrize("N", [1, 33, 257])
+def test_ragged_batches_take_the_plain_store_path(pkg, oracle, N):
+    """Batch sizes whose last 32-env group has an ODD row count: the mask rows of that group cannot leave through the
+    16-byte bulk copy and use the plain coalesced store; rows, observations and the fused env call must still match."""
+    P, seed = 2, 77
+    eng = pkg.BatchedSplendor(N, P, seed=seed, first_game=5, limit_rounds=True)
+    orcs = [oracle.init(P, *oracle.synth_game(seed, 5 + e, P)) for e in range(N)]
+    rng = np.random.default_rng(N)
+    guard = torch.full((N + 1, 110), 0x5A5A5A5A, dtype=torch.int32, device=eng.device)  # one spare row: no write past the end
+    for t in range(14):
+        mask = eng.legal_mask(out=guard[:N]).cpu().numpy()
+        assert (guard[N] == 0x5A5A5A5A).all()
+        obs = eng.observe().cpu().numpy()
+        act = np.zeros(N, np.int16)
+        for e in range(N):
+            legal = oracle.legal(orcs[e])
+            assert np.array_equal(unpack_mask(mask[e]), legal), (e, t)
+            assert np.array_equal(obs[e].view(np.uint32), oracle.observe(orcs[e], orcs[e].cur).view(np.uint32)), (e, t)
+            act[e] = rng.choice(legal)
+            oracle.step(orcs[e], int(act[e]))
+        eng.step(torch.from_numpy(act))
+    # the fused call (self-play form: acts for the seat to move, returns the next mover's rows)
+    act = np.array([rng.choice(oracle.legal(o)) for o in orcs], np.int16)
+    obs, rew, term, ill, mask = eng.env_step(None, torch.from_numpy(act), self_play=True)
+    mask, obs = mask.cpu().numpy(), obs.cpu().numpy()
+    for e in range(N):
+        oracle.step(orcs[e], int(act[e]))
+        assert np.array_equal(unpack_mask(mask[e]), oracle.legal(orcs[e])), e
+        assert np.array_equal(obs[e].view(np.uint32), oracle.observe(orcs[e], orcs[e].cur).view(np.uint32)), e
+
+
 @pytest.mark.parametrize("P", [2, 3, 4])
 def test_env_step_matches_oracle_emulation_of_splendor_env(pkg, oracle, P):
     """spl_env_step vs SplendorEnv.step semantics (splendor_env.py:127-231) emulated with the oracle: learner move,
