@@ -113,3 +113,33 @@ def undo(words, P, seat, index, card, noble, returned):
     nat.check(nat.lib().spl_undo(b["state"].data_ptr(), seat_t.data_ptr(), act_t.data_ptr(), card_t.data_ptr(), noble_t.data_ptr(),
                                  ret_t.data_ptr(), 1, P, _stream()), "spl_undo")
     words[:] = b["state"].cpu().numpy().view(np.uint32).reshape(-1)
+
+
+def minimax2(words, deck_lists, P, seat):
+    """MiniMaxAgent.SelectAction for `seat` on one state: (best ALL_ACTIONS index, best value, actions, values)."""
+    if P != 2:
+        raise ValueError("the minimax agent supports only a game of 2 players")
+    b = _buf(P)
+    _up(b, words, seat)
+    b["decks"].copy_(torch.from_numpy(np.asarray(deck_lists, np.uint8).reshape(1, 90)))
+    d = b["state"].device
+    counts = torch.zeros(1, dtype=torch.int32, device=d)
+    nat.check(nat.lib().spl_count_legal(b["state"].data_ptr(), counts.data_ptr(), 1, P, _stream()), "spl_count_legal")
+    M = int(counts.item())
+    offsets = torch.tensor([0, M], dtype=torch.int64, device=d)
+    child_value = torch.empty(M, dtype=torch.float64, device=d)
+    child_action = torch.empty(M, dtype=torch.int16, device=d)
+    best_action = torch.empty(1, dtype=torch.int16, device=d)
+    best_value = torch.empty(1, dtype=torch.float64, device=d)
+    nat.check(nat.lib().spl_minimax2(b["state"].data_ptr(), b["decks"].data_ptr(), 0, 0, None, offsets.data_ptr(), child_value.data_ptr(),
+                                     child_action.data_ptr(), best_action.data_ptr(), best_value.data_ptr(), 1, M, P, _stream()),
+              "spl_minimax2")
+    return int(best_action.item()), float(best_value.item()), child_action.cpu().numpy(), child_value.cpu().numpy()
+
+
+def minimax_eval(words, P, seat) -> float:
+    b = _buf(P)
+    _up(b, words, seat)
+    out = torch.empty(1, dtype=torch.float64, device=b["state"].device)
+    nat.check(nat.lib().spl_minimax_eval(b["state"].data_ptr(), None, out.data_ptr(), 1, P, _stream()), "spl_minimax_eval")
+    return float(out.item())

@@ -137,6 +137,8 @@ class SplendorVecEnv:
 
     self_play=True: no in-kernel opponents - every call applies the action of the seat to move (info["acted"]) and returns
     the next mover's observation and mask (info["my_id"]), so one policy can play all seats.
+    opponent="minimax" (2 players): the opponent is the reference's MiniMaxAgent (agents/our_agents/minmax.py), the default
+    PPO test opponent (arguments_parsing.py:107), searched on the GPU for all envs at once (spl_minimax2).
 
     reset()  -> (obs [N,265] f32, {"my_id": int8 [N]})
     step(a)  -> (obs, reward f32 [N], terminated bool [N], truncated bool [N] (always False), info)
@@ -147,7 +149,13 @@ class SplendorVecEnv:
     """
 
     def __init__(self, num_envs: int, num_agents: int = 2, seed: int = 1234, first_game: int = 0, shuffle_turns: bool = True,
-                 fixed_turn: int | None = None, device="cuda", raise_on_illegal: bool = False, self_play: bool = False):
+                 fixed_turn: int | None = None, device="cuda", raise_on_illegal: bool = False, self_play: bool = False,
+                 opponent: str = "random"):
+        if opponent not in ("random", "minimax"):
+            raise ValueError(f"unknown opponent {opponent!r}")
+        if opponent == "minimax" and (num_agents != 2 or self_play):
+            raise ValueError("the minimax opponent supports only a game of 2 players (and no self-play)")
+        self.opponent = opponent
         self.num_envs, self.number_of_players = int(num_envs), int(num_agents)
         self.engine = BatchedSplendor(num_envs, num_agents, seed=seed, first_game=first_game, limit_rounds=True, device=device)
         self.device = self.engine.device
@@ -182,6 +190,8 @@ class SplendorVecEnv:
         self.my_turn = self._draw_seats(self.num_envs).to(self.device)
         self._done.zero_()
         skip = torch.full((self.num_envs,), -1, dtype=torch.int16, device=self.device)
+        if self.opponent == "minimax":
+            self._minimax_opponents_move()
         obs, _, term, _, mask = self.engine.env_step(self.my_turn, skip, self_play=self.self_play)
         if self.self_play:
             self.my_turn = self._seat_to_move()
@@ -199,7 +209,14 @@ class SplendorVecEnv:
             self.my_turn = self.my_turn.clone()
             self.my_turn[self._done] = self._draw_seats(n).to(self.device)
             a = torch.where(self._done, torch.full_like(a, -1), a)
-        obs, reward, term, illegal, mask = self.engine.env_step(self.my_turn, a, self_play=self.self_play)
+        if self.opponent == "minimax":
+            # the learner's move alone (it is the seat to move wherever a >= 0), the searched reply, then the learner's rows
+            _, reward, _, illegal, _ = self.engine.env_step(None, a, want_mask=False, want_obs=False, self_play=True)
+            self._minimax_opponents_move()
+            skip = torch.full_like(a, -1)
+            obs, _, term, _, mask = self.engine.env_step(self.my_turn, skip)
+        else:
+            obs, reward, term, illegal, mask = self.engine.env_step(self.my_turn, a, self_play=self.self_play)
         acted = self.my_turn
         if self.self_play:
             self.my_turn = self._seat_to_move()
@@ -210,6 +227,15 @@ class SplendorVecEnv:
         self.legal_mask = mask
         info = {"legal_mask": mask, "illegal": illegal != 0, "my_id": self.my_turn, "end_kind": term, "acted": acted}
         return obs, reward.to(torch.float32), self._done.clone(), torch.zeros_like(self._done), info
+
+    def _minimax_opponents_move(self):
+        """Where the game goes on and it is not the learner's turn: one depth-2 minimax move of the opponent."""
+        skip = torch.full((self.num_envs,), -1, dtype=torch.int16, device=self.device)
+        _, _, term, _, _ = self.engine.env_step(None, skip, want_mask=False, want_obs=False, self_play=True)
+        need = (term == 0) & (self._seat_to_move() != self.my_turn)
+        if bool(need.any()):
+            best = self.engine.minimax2()[0]
+            self.engine.env_step(None, torch.where(need, best, skip), want_mask=False, want_obs=False, self_play=True)
 
     def _seat_to_move(self) -> torch.Tensor:
         return ((self.engine.state[1, :, 3] >> 20) & 3).to(torch.int8)

@@ -170,3 +170,89 @@ def test_gpu_minimax_on_fuzzed_states(pkg, oracle):
         assert np.array_equal(child_action[lo:hi], acts.astype(np.int16)), e
         assert np.array_equal(bits(child_value[lo:hi]), bits(vals)), e
         assert best_action[e] == select_best(acts, vals), e
+
+
+@pytest.mark.gpu
+def test_minimax_agent_class_plays_a_whole_game_like_the_oracle(pkg, oracle):
+    """The drop-in MiniMaxAgent (splendor-ai_b200/minimax.py) inside the reference-shaped Game loop against a RandomAgent:
+    every decision equals the oracle's depth-2 search on the replayed position, and the search agent wins."""
+    from splendor_ai_b200 import game_rule as G
+    from splendor_ai_b200 import minimax, template
+    from splendor_ai_b200.game import Game
+
+    assert minimax.myAgent is minimax.MiniMaxAgent
+    log = []
+
+    class LoggedSearch(minimax.MiniMaxAgent):
+        def SelectAction(self, actions, game_state, game_rule):
+            a = super().SelectAction(actions, game_state, game_rule)
+            log.append((self.id, G.action_index(a, game_state, self.id), self.last_value, self.evaluate(game_state)))
+            return a
+
+    class LoggedRandom(template.RandomAgent):
+        def SelectAction(self, actions, game_state, game_rule):
+            a = super().SelectAction(actions, game_state, game_rule)
+            log.append((self.id, G.action_index(a, game_state, self.id), None, None))
+            return a
+
+    g = Game(G.SplendorGameRule, [LoggedSearch(0), LoggedRandom(1)], 2, seed=5, agents_namelist=["minimax", "random"], time_limit=60)
+    st = g.game_rule.current_game_state
+    s = oracle.init(2, st._deck_lists.copy(), [G.NOBLE_ID[n[0]] for n in st.board.nobles])
+    h = g.Run()
+    assert len(log) == len(h["actions"]) > 20
+    n_search = 0
+    for seat, idx, value, ev in log:
+        assert seat == s.cur
+        if seat == 0:
+            acts, vals = oracle.minimax2(s)
+            assert idx == select_best(acts, vals) and value == vals.max() and ev == oracle.minimax_eval(s, 0), n_search
+            n_search += 1
+        assert oracle.step(s, idx) >= 0
+    assert n_search >= 10 and h["scores"][0] > h["scores"][1]
+
+
+@pytest.mark.gpu
+def test_vec_env_with_minimax_opponent_matches_oracle_emulation(pkg, oracle):
+    """SplendorVecEnv(opponent="minimax"): learner move, the opponent's depth-2 search reply, the learner's next rows -
+    against the same loop written with the oracle (100-round cap, next-step auto-reset left out: 40 calls per env)."""
+    import torch
+
+    from splendor_ai_b200.env import SplendorVecEnv, unpack_mask
+
+    N, seed = 48, 99
+    env = SplendorVecEnv(N, 2, seed=seed, opponent="minimax")
+    obs, info = env.reset(seed=3)
+    me = info["my_id"].cpu().numpy()
+    orcs = [oracle.init(2, *oracle.synth_game(seed, e, 2)) for e in range(N)]
+
+    def reply(o, e):
+        if o.cur != me[e] and not oracle.game_ends(o, True):
+            acts, vals = oracle.minimax2(o)
+            oracle.step(o, select_best(acts, vals))
+
+    for e, o in enumerate(orcs):
+        reply(o, e)
+    rng = np.random.default_rng(0)
+    alive = np.ones(N, bool)
+    for t in range(40):
+        mask = unpack_mask(info["legal_mask"], torch.uint8).cpu().numpy()
+        obs_np = obs.cpu().numpy()
+        act = np.zeros(N, np.int16)
+        for e, o in enumerate(orcs):
+            if not alive[e]:
+                continue
+            legal = oracle.legal(o, int(me[e]))
+            assert np.array_equal(np.nonzero(mask[e])[0], legal), (e, t)
+            assert np.array_equal(obs_np[e].view(np.uint32), oracle.observe(o, int(me[e])).view(np.uint32)), (e, t)
+            act[e] = rng.choice(legal)
+        obs, reward, terminated, truncated, info = env.step(torch.from_numpy(act))
+        reward, terminated = reward.cpu().numpy(), terminated.cpu().numpy()
+        for e, o in enumerate(orcs):
+            if not alive[e]:
+                continue
+            assert reward[e] == oracle.step(o, int(act[e])), (e, t)
+            reply(o, e)
+            assert bool(terminated[e]) == bool(oracle.game_ends(o, True)), (e, t)
+            if terminated[e]:
+                alive[e] = False  # the next call resets this env; the emulation stops following it
+    assert alive.sum() < N  # the searched opponent finished some games inside 40 calls
