@@ -22,6 +22,14 @@ for P in (2, 3, 4):
         child, a2, rew, par, off = eng.expand()
         child.legal_mask()
         eng.final_scores()
+        eng.minimax_eval()
+        if P == 2:
+            eng.minimax2()
+            menv = SplendorVecEnv(N, 2, seed=4, opponent="minimax")
+            mo, minfo = menv.reset()
+            for t in range(3):
+                ma, _ = masked_sample(torch.randn((N, 3510), device="cuda"), minfo["legal_mask"], 3, t)
+                mo, _, _, _, minfo = menv.step(ma)
         seats = ((eng.state[1, :, 3] >> 20) & 3).to(torch.int8)
         eng.env_step(torch.zeros(N, dtype=torch.int8), torch.full((N,), -1, dtype=torch.int16))
         eng.env_step(None, torch.full((N,), -1, dtype=torch.int16), self_play=True)
