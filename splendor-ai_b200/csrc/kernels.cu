@@ -1,8 +1,8 @@
 // kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/splendor_b200.h.
 //
-//   playout_kernel      thread-per-game, state in registers for the whole game: reset -> {terminal test, legal count,
+//   playout_kernel      one thread = one game, state in registers for the whole game: reset -> {terminal test, legal count,
 //                       Philox choice, k-th legal action, apply} x steps -> calScore -> counters.  No HBM traffic inside
-//                       the loop except the optional trace.
+//                       the loop except the optional trace; the hardware block scheduler refills finished blocks.
 //   legal_mask_kernel   persistent; one thread builds one env's 3510-bit row in registers (32/64-bit group patterns) and
 //                       flushes finished words into its warp's dense shared-memory tile; lane 0 sends the warp's 32 rows
 //                       (14,080 contiguous bytes) to HBM with one bulk copy (cp.async.bulk) while the warp moves on.
@@ -117,72 +117,70 @@ __device__ __forceinline__ uint32_t turns_total(const Env<P> &e)
     return t;
 }
 
+// ONE GAME PER THREAD, one launch = n_games threads in blocks of `blk`.  The hardware block scheduler is the refill
+// mechanism: as soon as the slowest game of a block ends, a fresh block takes its place, so every SM always holds as
+// many games as its registers allow, and the 32 games of a warp stay in the same phase (reset together, step together,
+// score together).  An earlier persistent form (lanes drew their next game themselves) left each lane of a warp in a
+// different phase - reset / finalize ran one lane at a time and the instruction cache thrashed - and was 25-40 % slower
+// on large sweeps (profiles/r1_playout_ncu.md).
 template <int P, bool FRESH, bool COMPACT>
-__global__ void __launch_bounds__(BLOCK) playout_kernel(const PlayoutArgs a)
+__global__ void __launch_bounds__(BLOCK, COMPACT ? 7 : 5) playout_kernel(const PlayoutArgs a)  // 72 / 96 registers
 {
     __shared__ Tables sT;
     __shared__ unsigned long long sctr[16];
     if (threadIdx.x < 16) sctr[threadIdx.x] = 0;
     stage_tables(sT);
 
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool done = g >= a.n_games, have = false;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = g < a.n_games;
     Env<P> e;
-    int t = 0, t_end = 0;
-    DeckSrc src{nullptr, a.seed, 0};
-
-    while (!__all_sync(0xFFFFFFFFu, done)) {
-        if (!done) {
-            if (!have) {  // next game of this lane
-                src.game = (!FRESH && a.game_ids) ? a.game_ids[g] : a.first_game + (uint64_t)g;
-                if (FRESH) reset_env(e, a.seed, src.game);
-                else {
-                    load_env(e, a.state, a.n_games, g);
-                    src.lists = a.decks ? a.decks + g * SPL_DECK_BYTES : nullptr;
-                }
-                t = (int)turns_total(e);
-                t_end = t + a.max_steps;
-                have = true;
-            }
-            int kind = game_ends(e, a.flags);
-            if (kind == SPL_END_NONE && t >= t_end) kind = SPL_END_TRUNCATED;
-            if (kind == SPL_END_NONE) {
-                Ctx c;
-                FamilyCounts f;
-                Choice ch;
-                const uint32_t r = philox_inline(a.seed, src.game, (uint32_t)t, STREAM_ACTION).x;
-                make_ctx(e, sT, c);
-                const int total = count_legal<P, COMPACT>(e, sT, c, f);
-                select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
-                if (a.trace && t < a.trace_len) a.trace[(int64_t)t * a.n_games + g] = (int16_t)ch.idx;
-                apply_action(e, ch, src);
-                t++;
-            } else {  // game over: calScore, win/tie/loss, counters, outputs
-                int sc[P], oc[P];
-                final_scores(e, sc, oc);
-                unsigned long long nob = 0, sum = 0;
-#pragma unroll
-                for (int p = 0; p < P; p++) {
-                    if (a.score2) a.score2[g * P + p] = (int8_t)sc[p];
-                    if (oc[p] == 2) atomicAdd(&sctr[SPL_CTR_WINS + p], 1ull);
-                    if (oc[p] == 1) atomicAdd(&sctr[SPL_CTR_TIES + p], 1ull);
-                    sum += (unsigned)sc[p];
-                    nob += __popc(e.pi[p] >> 16 & 0x3FFu);
-                }
-                atomicAdd(&sctr[SPL_CTR_GAMES], 1ull);
-                atomicAdd(&sctr[SPL_CTR_STEPS], (unsigned long long)t);
-                atomicAdd(&sctr[SPL_CTR_END_SCORE - 1 + kind], 1ull);
-                atomicAdd(&sctr[SPL_CTR_SCORE2_SUM], sum);
-                atomicAdd(&sctr[SPL_CTR_NOBLES], nob);
-                if (a.steps) a.steps[g] = (int16_t)t;
-                if (a.end_kind) a.end_kind[g] = (uint8_t)kind;
-                if (a.state) store_env(e, a.state, a.n_games, g);
-                have = false;
-                g += stride;
-                done = g >= a.n_games;
-            }
+    int t = 0, kind = SPL_END_NONE;
+    if (live) {
+        DeckSrc src{nullptr, a.seed, (!FRESH && a.game_ids) ? a.game_ids[g] : a.first_game + (uint64_t)g};
+        if (FRESH) reset_env(e, a.seed, src.game);
+        else {
+            load_env(e, a.state, a.n_games, g);
+            src.lists = a.decks ? a.decks + g * SPL_DECK_BYTES : nullptr;
         }
+        t = (int)turns_total(e);
+        const int t_end = t + a.max_steps;
+        for (;;) {
+            kind = game_ends(e, a.flags);
+            if (kind == SPL_END_NONE && t >= t_end) kind = SPL_END_TRUNCATED;
+            if (kind != SPL_END_NONE) break;
+            Ctx c;
+            FamilyCounts f;
+            Choice ch;
+            const uint32_t r = philox_inline(a.seed, src.game, (uint32_t)t, STREAM_ACTION).x;
+            make_ctx(e, sT, c);
+            const int total = count_legal<P, COMPACT>(e, sT, c, f);
+            select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
+            if (a.trace && t < a.trace_len) a.trace[(int64_t)t * a.n_games + g] = (int16_t)ch.idx;
+            apply_action(e, ch, src);
+            t++;
+        }
+    }
+    // the warp is back together: calScore, win/tie/loss, counters, outputs
+    if (live) {
+        int sc[P], oc[P];
+        final_scores(e, sc, oc);
+        unsigned long long nob = 0, sum = 0;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            if (a.score2) a.score2[g * P + p] = (int8_t)sc[p];
+            if (oc[p] == 2) atomicAdd(&sctr[SPL_CTR_WINS + p], 1ull);
+            if (oc[p] == 1) atomicAdd(&sctr[SPL_CTR_TIES + p], 1ull);
+            sum += (unsigned)sc[p];
+            nob += __popc(e.pi[p] >> 16 & 0x3FFu);
+        }
+        atomicAdd(&sctr[SPL_CTR_GAMES], 1ull);
+        atomicAdd(&sctr[SPL_CTR_STEPS], (unsigned long long)t);
+        atomicAdd(&sctr[SPL_CTR_END_SCORE - 1 + kind], 1ull);
+        atomicAdd(&sctr[SPL_CTR_SCORE2_SUM], sum);
+        atomicAdd(&sctr[SPL_CTR_NOBLES], nob);
+        if (a.steps) a.steps[g] = (int16_t)t;
+        if (a.end_kind) a.end_kind[g] = (uint8_t)kind;
+        if (a.state) store_env(e, a.state, a.n_games, g);
     }
     __syncthreads();
     if (a.counters && threadIdx.x < 16 && sctr[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], sctr[threadIdx.x]);
@@ -931,12 +929,12 @@ static int launch_playout(bool fresh, const PlayoutArgs &a, int P, cudaStream_t 
         blk = s ? atoi(s) : PLAYOUT_BLOCK;
         if (blk != 32 && blk != 64 && blk != 96 && blk != 128) blk = PLAYOUT_BLOCK;
     }
-    const int64_t want = (a.n_games + blk - 1) / blk, cap = (int64_t)sm_count() * (1024 / blk);
-    const unsigned grid = (unsigned)(want < cap ? want : cap);
-    // large sweeps (every lane plays many games, warps drift apart) run the size-optimised instantiation
+    // two instantiations: the register-lean one (rolled buy loop, 72 registers: 7 blocks per SM instead of 6) wins as soon
+    // as the launch fills the GPU more than once; below that the faster straight-line code wins
     static int force = -1;
     if (force < 0) { const char *s = getenv("SPL_PLAYOUT_COMPACT"); force = s ? (atoi(s) ? 1 : 0) : 2; }
-    const bool compact = force == 2 ? a.n_games >= 4 * (int64_t)grid * blk : force == 1;
+    const unsigned grid = (unsigned)((a.n_games + blk - 1) / blk);
+    const bool compact = force == 2 ? (int64_t)grid * blk > (int64_t)sm_count() * 640 : force == 1;
     if (fresh && compact) { DISPATCH_P(P, playout_kernel<PP, true, true><<<grid, blk, 0, stream>>>(a)); }
     else if (fresh) { DISPATCH_P(P, playout_kernel<PP, true, false><<<grid, blk, 0, stream>>>(a)); }
     else if (compact) { DISPATCH_P(P, playout_kernel<PP, false, true><<<grid, blk, 0, stream>>>(a)); }
