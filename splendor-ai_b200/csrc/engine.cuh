@@ -69,6 +69,10 @@ struct Tables {
     uint16_t cwr2_pair[2][16];  // [k==4][x]: k others held>=1 -> bits of the i<j entries of combinations_with_replacement(k,2)
     uint16_t cwr2_dbl[2][16];   // [k==4][y]: held>=2 -> bits of the (i,i) entries
     uint16_t cwr3[512];         // k=3: x | y<<3 | z<<6 (held >=1/>=2/>=3) -> bits of combinations_with_replacement(3,3)
+    // return-multiset generating functions (see ReturnPoly below): (1 + x + .. + x^lvl)^n and 1 / (1 + x + .. + x^lvl)
+    // as base-256 digit strings modulo 2^32
+    uint32_t poly_pow[3][8];    // [lvl-1][n], n = 0..6
+    uint32_t poly_inv[4];       // [lvl]
 };
 
 namespace detail {
@@ -210,6 +214,16 @@ __host__ __device__ constexpr Tables make_tables()
                     if (ok) bits |= 1 << r;
                 }
         T.cwr3[v] = (uint16_t)bits;
+    }
+    const uint32_t unit[4] = {0x00000001u, 0x00000101u, 0x00010101u, 0x01010101u};
+    for (int l = 1; l <= 3; l++) {
+        uint32_t p = 1;
+        for (int n = 0; n < 8; n++) { T.poly_pow[l - 1][n] = p; p *= unit[l]; }
+    }
+    for (int l = 0; l < 4; l++) {  // Newton iteration for the inverse of an odd number modulo 2^32
+        uint32_t x = unit[l];
+        for (int it = 0; it < 5; it++) x *= 2u - unit[l] * x;
+        T.poly_inv[l] = x;
     }
     return T;
 }
@@ -457,35 +471,14 @@ __device__ __forceinline__ void make_ctx(const Env<P> &e, const Tables &T, Ctx &
     c.Lmin = c.hold <= 7 ? c.Lmax : (c.hold == 8 ? min(c.nA, 2) : min(c.nA, 1));
 }
 
-// Family totals, per-length collect_diff totals and per-slot buy counts of one decision.
+// Family totals, per-group collect counts and per-slot buy counts of one decision.
 struct FamilyCounts {
     int res, same, diff, bres, bav;  // actions per family (noble multiplicity included)
-    int dL[3];                       // collect_diff actions taking 1 / 2 / 3 gems
+    uint32_t grp[9];                 // return variants per collect group, one byte each, in ALL_ACTIONS order:
+                                     // bytes 0..4 the collect_same colours, bytes 8..32 the collect_diff combos 0..24
     uint32_t buy_lo, buy_hi;         // buy actions per card, 4 bits each: board slots 0..7 | slots 8..11 + reserved 0..2
 };
 
-// binomial(n, L) for n <= 5 (negative n -> 0), L a compile-time 1..3
-template <int L>
-__device__ __forceinline__ int binom(int n)
-{
-    n = max(n, 0);
-    if (L == 1) return n;
-    return (int)(((L == 2 ? 0xA63100u : 0xA41000u) >> (4 * n)) & 15u);
-}
-__device__ __forceinline__ int choose2(int x) { return (x * (x - 1)) >> 1; }
-__device__ __forceinline__ int choose3(int x) { return (x * (x - 1) * (x - 2) * 10923) >> 16; }  // exact for x <= 40
-
-// Number of distinct multisets of e (0..3) gems the agent can return out of colours O, given how many of those colours
-// it holds >=1 / >=2 / >=3 of (generate_return_combos :329-367).  Branch-free.
-__device__ __forceinline__ int n_returns(int e, int a1, int a2, int a3)
-{
-    const int r2 = choose2(a1) + a2, r3 = choose3(a1) + a2 * (a1 - 1) + a3;
-    return e <= 0 ? 1 : (e == 1 ? a1 : (e == 2 ? r2 : r3));
-}
-__device__ __forceinline__ int n_returns(int e, const Ctx &c, uint32_t O)
-{
-    return n_returns(e, __popc(c.h1 & O), __popc(c.h2 & O), __popc(c.h3 & O));
-}
 __device__ __forceinline__ int reserve_variants(const Ctx &c)
 {
     return (!c.bank_yellow || c.hold < 10) ? 1 : __popc(c.h1 & NORMAL_FIELDS);
@@ -522,30 +515,78 @@ __device__ __forceinline__ bool can_buy(const Ctx &c, uint2 cw, uint32_t &pay)
     return field(c.cards, cw.y & 31u) != 7u && wild <= (uint32_t)c.yellow;
 }
 
-// collect_diff actions that take exactly L gems (before the noble multiplicity), in closed form.
-// Instead of looping over the colour combinations C and counting the return multisets R each one allows, sum over the
-// (few) classes of R: a multiset whose support meets the available colours A in j colours is compatible with
-// binomial(nA - j, L) combinations.  M[j] = number of feasible R of size e with |supp(R) & A| = j, from
-//   q_i = colours of A held >= i times,  r_i = other colours (yellow, or bank empty) held >= i times.
-template <int L>
-__device__ __forceinline__ int diff_count(const Ctx &c, int q1, int q2, int q3, int r1, int r2, int r3)
+// ---- collect_same / collect_diff return variants as generating functions
+// The return multisets of e gems out of a colour set O, with at most min(held_c, 3) of colour c, are counted by the
+// coefficient of x^e in  prod_{c in O} (1 + x + .. + x^lvl_c),  lvl_c = min(held_c, 3)  (generate_return_combos
+// :329-367 builds exactly these multisets).  Only e <= 3 matters, and every coefficient up to x^3 is < 256 (at most
+// C(8,3) = 56), so a polynomial mod x^4 is kept as four base-256 digits of one 32-bit word: the product of two
+// polynomials is ONE integer multiply (digits never carry; the x^4.. terms fall off the top), and removing a colour
+// is a multiply by the modular inverse of its factor (the factors are odd numbers: 1/(1+x) = 0xFF00FF01 ...).
+// So with G = the product over all six colours, a collect group that takes the colours {a,b,c} has
+//     variants = digit_e( G * I_a * I_b * I_c ),   e = gems over the limit of 10 (digit 0 is 1: "return nothing"),
+// and an unavailable colour (bank empty, or < 4 for collect_same) is folded in as I = 0, which zeroes the whole group.
+// 38 multiplies and 21 byte permutes give all 30 groups of a decision at once, packed one byte per group in
+// ALL_ACTIONS order; select_legal finds the k-th action with two SWAR prefix-sum steps instead of walking the groups.
+__device__ __forceinline__ uint32_t pick2(uint32_t x, uint32_t y, uint32_t sel) { return __byte_perm(x, y, sel); }
+__device__ __forceinline__ uint32_t pack4(uint32_t xy, uint32_t zw) { return __byte_perm(xy, zw, 0x5410u); }
+
+__device__ __forceinline__ void collect_groups(const Tables &T, const Ctx &c, FamilyCounts &f)
 {
-    const int e = c.hold + L - 10;  // gems to return; <= L
-    int m0 = 1, m1 = 0, m2 = 0, m3 = 0;
-    if (L >= 1) { const bool s = e == 1; m0 = s ? r1 : m0; m1 = s ? q1 : m1; }
-    if (L >= 2) {
-        const bool s = e == 2;
-        m0 = s ? r2 + choose2(r1) : m0; m1 = s ? q2 + q1 * r1 : m1; m2 = s ? choose2(q1) : m2;
+    const int t1 = __popc(c.h1), t2 = __popc(c.h2), t3 = __popc(c.h3);
+    SPL_CHECK(t1 >= t2 && t2 >= t3 && t1 <= 6 && c.hold <= 10);
+    const uint32_t G = T.poly_pow[0][t1 - t2] * T.poly_pow[1][t2 - t3] * T.poly_pow[2][t3];
+    uint32_t Js[5], Jd[5];  // inverse factor of normal colour n, zero when collect_same / collect_diff cannot take it
+#pragma unroll
+    for (int n = 0; n < 5; n++) {
+        const int fl = field_of_normal(n);
+        const uint32_t inv = T.poly_inv[min(field(c.gems, 5 * fl), 3u)];
+        Js[n] = (c.A4 >> fl & 1u) ? inv : 0u;
+        Jd[n] = (c.A1 >> fl & 1u) ? inv : 0u;
     }
-    if (L >= 3) {
-        const bool s = e == 3;
-        m0 = s ? r3 + r2 * (r1 - 1) + choose3(r1) : m0;
-        m1 = s ? q3 + q2 * r1 + r2 * q1 + q1 * choose2(r1) : m1;
-        m2 = s ? q2 * (q1 - 1) + choose2(q1) * r1 : m2;
-        m3 = s ? choose3(q1) : m3;
+    // digit selectors: a group taking L gems returns e_L = max(hold + L - 10, 0) <= 3; collect_same returns e_2
+    const uint32_t e1 = (uint32_t)max(c.hold - 9, 0), e2 = (uint32_t)max(c.hold - 8, 0), e3 = (uint32_t)max(c.hold - 7, 0);
+    const uint32_t s11 = e1 * 17u + 0x40u, s12 = e1 + e2 * 16u + 0x40u, s22 = e2 * 17u + 0x40u, s23 = e2 + e3 * 16u + 0x40u,
+                   s33 = e3 * 17u + 0x40u;
+    // collect_same (:475-496): colour n excluded from the returnable colours
+    {
+        const uint32_t p0 = G * Js[0], p1 = G * Js[1], p2 = G * Js[2], p3 = G * Js[3], p4 = G * Js[4];
+        f.grp[0] = pack4(pick2(p0, p1, s22), pick2(p2, p3, s22));
+        f.grp[1] = pick2(p4, 0u, e2 + 0x4440u);
     }
-    const int n = m0 * binom<L>(c.nA) + m1 * binom<L>(c.nA - 1) + m2 * binom<L>(c.nA - 2) + m3 * binom<L>(c.nA - 3);
-    return (L >= c.Lmin && L <= c.Lmax) ? n : 0;
+    // collect_diff (:437-473): the sizes outside [Lmin, Lmax] are zeroed through G (sizes above Lmax contain an
+    // unavailable colour anyway)
+    {
+        const uint32_t G1 = c.Lmin <= 1 ? G : 0u, G2 = c.Lmin <= 2 ? G : 0u, G3 = G;
+        uint32_t a[5], b[10], d[10];
+#pragma unroll
+        for (int n = 0; n < 5; n++) a[n] = G1 * Jd[n];
+        uint32_t pr[10];
+        {
+            int i = 0;
+#pragma unroll
+            for (int x = 0; x < 5; x++)
+#pragma unroll
+                for (int y = x + 1; y < 5; y++) pr[i++] = Jd[x] * Jd[y];  // 01 02 03 04 12 13 14 23 24 34
+        }
+#pragma unroll
+        for (int i = 0; i < 10; i++) b[i] = G2 * pr[i];
+        const uint32_t g0 = G3 * Jd[0], g1 = G3 * Jd[1], g2 = G3 * Jd[2];
+        d[0] = g0 * pr[4]; d[1] = g0 * pr[5]; d[2] = g0 * pr[6];   // 012 013 014
+        d[3] = g0 * pr[7]; d[4] = g0 * pr[8]; d[5] = g0 * pr[9];   // 023 024 034
+        d[6] = g1 * pr[7]; d[7] = g1 * pr[8]; d[8] = g1 * pr[9];   // 123 124 134
+        d[9] = g2 * pr[9];                                         // 234
+        f.grp[2] = pack4(pick2(a[0], a[1], s11), pick2(a[2], a[3], s11));
+        f.grp[3] = pack4(pick2(a[4], b[0], s12), pick2(b[1], b[2], s22));
+        f.grp[4] = pack4(pick2(b[3], b[4], s22), pick2(b[5], b[6], s22));
+        f.grp[5] = pack4(pick2(b[7], b[8], s22), pick2(b[9], d[0], s23));
+        f.grp[6] = pack4(pick2(d[1], d[2], s33), pick2(d[3], d[4], s33));
+        f.grp[7] = pack4(pick2(d[5], d[6], s33), pick2(d[7], d[8], s33));
+        f.grp[8] = pick2(d[9], 0u, e3 + 0x4440u);
+    }
+    // totals: bytes are <= 15, so whole words can be added before the horizontal byte sum
+    f.same = (int)((((f.grp[0] + f.grp[1]) * 0x01010101u) >> 24) * (uint32_t)c.nS);
+    const uint32_t dsum = f.grp[2] + f.grp[3] + f.grp[4] + f.grp[5] + f.grp[6] + f.grp[7] + f.grp[8];  // bytes <= 70
+    f.diff = (int)(((dsum * 0x01010101u) >> 24) * (uint32_t)c.nS);
 }
 
 // COMPACT = smaller code (rolled loops) for launches where warps are spread over reset / step / finalize and the
@@ -554,24 +595,7 @@ template <int P, bool COMPACT = false>
 __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, const Ctx &c, FamilyCounts &f)
 {
     f.res = c.n_resv < 3 ? __popc(c.occ) * c.nS * reserve_variants(c) : 0;
-    const int t1 = __popc(c.h1), t2 = __popc(c.h2), t3 = __popc(c.h3);
-    // collect_same (:475-496): colour fl excluded from the returnable colours
-    int same = 0;
-#pragma unroll
-    for (int n = 0; n < 5; n++) {
-        const int fl = field_of_normal(n);
-        const int nv = n_returns(c.hold - 8, t1 - (int)(c.h1 >> fl & 1u), t2 - (int)(c.h2 >> fl & 1u), t3 - (int)(c.h3 >> fl & 1u));
-        same += (c.A4 >> fl & 1u) ? nv : 0;
-    }
-    f.same = same * c.nS;
-    // collect_diff (:437-473)
-    {
-        const int q1 = __popc(c.h1 & c.A1), q2 = __popc(c.h2 & c.A1), q3 = __popc(c.h3 & c.A1);
-        f.dL[0] = diff_count<1>(c, q1, q2, q3, t1 - q1, t2 - q2, t3 - q3) * c.nS;
-        f.dL[1] = diff_count<2>(c, q1, q2, q3, t1 - q1, t2 - q2, t3 - q3) * c.nS;
-        f.dL[2] = diff_count<3>(c, q1, q2, q3, t1 - q1, t2 - q2, t3 - q3) * c.nS;
-        f.diff = f.dL[0] + f.dL[1] + f.dL[2];
-    }
+    collect_groups(T, c, f);
     // buy (:522-568): 12 board slots + 3 reserved cards, branch-free; empty slots (0xFF) index an unaffordable filler
     const uint32_t eff = (c.gems & ~(31u << YSH)) + c.cards;    // gems + bought cards per colour (<= 14)
     const uint32_t cap = ((c.cards + 9u * ONES6) & H6) | (16u << YSH);  // guard bit set where 7 cards of the colour are owned (+ filler)
@@ -647,51 +671,48 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
     }
     k -= f.res;
     if (k < f.same + f.diff) {
-        // collect_same (510 + c*126 + n*21 + v) and collect_diff (combo_base + n*V + v): find the group (colour or colour
-        // combination), then the noble slot and the vi-th feasible return variant within a range of its table row
+        // collect_same (510 + c*126 + n*21 + v) and collect_diff (combo_base + n*V + v).  The 30 groups (colours, then
+        // colour combinations) lie in index order in f.grp, one byte of return-variant count each; a group holds
+        // variants * nS consecutive legal actions.  Find the group of action k in two prefix-sum steps - the word, then
+        // the byte inside it (a multiply by 0x01010101 turns four counts into their four running sums) - then the noble
+        // slot and the vi-th payable return variant of the group's table row.
+        const uint32_t q = (uint32_t)small_div(k, c.nS);
+        uint32_t W = f.grp[0], before = 0, run = 0;
+        int wi = 0;
+#pragma unroll
+        for (int w = 0; w < 9; w++) {
+            if (w > 0 && q >= run) { W = f.grp[w]; before = run; wi = w; }
+            run += (f.grp[w] * 0x01010101u) >> 24;
+        }
+        SPL_CHECK(q < run && q - before < 64u);
+        const uint32_t sums = W * 0x01010101u;                                    // running sums of the word's bytes (<= 60)
+        const uint32_t ahead = (((q - before) * 0x01010101u | 0x80808080u) - sums) & 0x80808080u;  // bytes wholly before q
+        const int b = __popc(ahead), g = 4 * wi + b;
+        SPL_CHECK(b < 4 && g != 5 && g != 6 && g != 7 && g <= 32);
+        before += ((sums << 8) >> (8 * b)) & 255u;
+        const int nv = (int)((W >> (8 * b)) & 255u);
+        k -= (int)before * c.nS;
         const uint32_t *row;
-        int base, V, nv = 1;
+        int base, V;
         uint32_t vbits;
-        if (k < f.same) {
-            const int e2 = c.hold - 8;
-            int col = 0;
-            for (; col < 4; col++) {
-                const int fl = field_of_normal(col);
-                if (!(c.A4 >> fl & 1)) continue;
-                nv = n_returns(e2, c, 63u & ~(1u << fl));
-                if (k < nv * c.nS) break;
-                k -= nv * c.nS;
-            }
-            if (col == 4) nv = n_returns(e2, c, 63u & ~(1u << field_of_normal(4)));
+        if (g < 8) {
+            const int col = g, e2 = c.hold - 8;
             row = T.ret_same + col * 21;
             base = BASE_SAME + col * 126; V = 21;
             vbits = same_variant_bits(T, c, col, e2);
             ch.type = T_SAME; ch.slot = col;
             ch.C = 2u << (5 * field_of_normal(col));
         } else {
-            k -= f.same;
-            int L = 1;
-            if (k >= f.dL[0]) { k -= f.dL[0]; L = 2; if (k >= f.dL[1]) { k -= f.dL[1]; L = 3; } }
-            const int ex = c.hold + L - 10;
-            int ci = L == 1 ? 0 : (L == 2 ? 5 : 15);
-            const int ci_end = L == 1 ? 4 : (L == 2 ? 14 : 24);
-            for (; ci < ci_end; ci++) {  // the last candidate needs no test
-                const uint32_t m = T.combo_mask[ci];
-                if (m & ~c.A1) continue;
-                nv = ex <= 0 ? 1 : n_returns(ex, c, 63u & ~m);
-                if (k < nv * c.nS) break;
-                k -= nv * c.nS;
-            }
-            if (ci == ci_end && ex > 0) nv = n_returns(ex, c, 63u & ~(uint32_t)T.combo_mask[ci]);
+            const int ci = g - 8, L = combo_len(ci);
             V = L == 1 ? 6 : (L == 2 ? 15 : 20);
             row = T.ret_diff + T.combo_off[ci];
             base = T.combo_base[ci];
-            vbits = diff_variant_bits(T, c, ci, L, ex);
+            vbits = diff_variant_bits(T, c, ci, L, c.hold + L - 10);
             ch.type = T_DIFF; ch.slot = ci;
             ch.C = T.combo_c[ci];
         }
         const int ni = small_div(k, nv), vi = k - ni * nv;
-        SPL_CHECK(nv >= 1 && vi >= 0 && vi < __popc(vbits) && ni < c.nS);
+        SPL_CHECK(nv >= 1 && nv == __popc(vbits) && vi >= 0 && vi < nv && ni < c.nS);
         const int v = select_bit(vbits, vi);  // the vi-th payable return variant, ascending
         SPL_CHECK(v < V);
         ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
@@ -807,7 +828,8 @@ __device__ __forceinline__ int apply_action(Env<P> &e, const Choice &ch, const D
     e.bank = e.bank - ch.C + ch.R;
     SPL_CHECK(!(g & H6) && !(e.bank & H6) && hsum6(g) <= 10);
     int score = 0;
-    if (ch.type == T_RESERVE || ch.type == T_BUY_AVAILABLE) {
+    // one test, not two short-circuit branches: the reserving and the buying lanes of a warp must enter the deal together
+    if ((1u << ch.type) & (1u << T_RESERVE | 1u << T_BUY_AVAILABLE)) {
         const int tier = ch.slot >> 2, col = ch.slot & 3;
         uint32_t w = e.d[0];
         if (tier == 1) w = e.d[1];

@@ -20,6 +20,18 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)  // PTX prmt.b32, default mode
+{
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t sel = (s >> (4 * i)) & 15u;
+        uint32_t byte = (uint32_t)(v >> (8 * (sel & 7u))) & 255u;
+        if (sel & 8u) byte = (byte & 0x80u) ? 255u : 0u;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __uint_as_float(uint32_t b) { float f; std::memcpy(&f, &b, 4); return f; }
