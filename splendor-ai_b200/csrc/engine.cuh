@@ -455,8 +455,8 @@ __device__ __forceinline__ void make_ctx(const Env<P> &e, const Tables &T, Ctx &
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const uint32_t d = satsub6(T.noble[(e.meta >> (4 * k)) & 15u], c.cards);
-        if (d == 0) c.S |= 1u << k;
-        else if ((d & (d - 1)) == 0 && (d & ONES6)) c.near |= 1u << (__ffs(d) - 1 + k);
+        c.S |= (d == 0 ? 1u : 0u) << k;
+        c.near |= ((d & (d - 1)) == 0 ? d & ONES6 : 0u) << k;  // exactly one gem of one colour short (branch-free)
     }
     c.nS = c.S ? __popc(c.S) : 1;
     c.hold = (int)hsum6(c.gems);
@@ -598,7 +598,15 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
     collect_groups(T, c, f);
     // buy (:522-568): 12 board slots + 3 reserved cards, branch-free; empty slots (0xFF) index an unaffordable filler
     const uint32_t eff = (c.gems & ~(31u << YSH)) + c.cards;    // gems + bought cards per colour (<= 14)
-    const uint32_t cap = ((c.cards + 9u * ONES6) & H6) | (16u << YSH);  // guard bit set where 7 cards of the colour are owned (+ filler)
+    // actions per buyable card of each colour = nobles to choose from after the purchase (at least 1), as a 5-bit field
+    // per colour; 0 where 7 cards of the colour are owned (the cap) and for the filler's "yellow"
+    uint32_t mult = 0;
+#pragma unroll
+    for (int n = 0; n < 5; n++) {
+        const int sh = 5 * field_of_normal(n);
+        mult |= (uint32_t)max(__popc(c.S | ((c.near >> sh) & 31u)), 1) << sh;
+    }
+    mult &= ~((((c.cards + 9u * ONES6) & H6) >> 4) * 31u);
     uint32_t lo = 0, hi = 0;
     if (!COMPACT) {
 #pragma unroll
@@ -607,8 +615,7 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
         const uint2 cw = T.card[(w >> (8 * (s & 3))) & 127u];
         const uint32_t sh = cw.y & 31u;
         const uint32_t wild = hsum6_small(satsub6(cw.x, eff));   // max(cost - cards - gems, 0) summed = wilds needed
-        const bool ok = wild <= (uint32_t)c.yellow && !((cap >> sh) & 16u);
-        const uint32_t cnt = ok ? (uint32_t)max(__popc(c.S | ((c.near >> sh) & 31u)), 1) : 0u;
+        const uint32_t cnt = wild <= (uint32_t)c.yellow ? (mult >> sh) & 31u : 0u;
         if (s < 8) lo |= cnt << (4 * s); else hi |= cnt << (4 * (s - 8));
     }
     } else {
@@ -624,8 +631,7 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
             const uint2 cw = T.card[(w >> (8 * b)) & 127u];
             const uint32_t sh = cw.y & 31u;
             const uint32_t wild = hsum6_small(satsub6(cw.x, eff));   // max(cost - cards - gems, 0) summed = wilds needed
-            const bool ok = wild <= (uint32_t)c.yellow && !((cap >> sh) & 16u);
-            gw |= (ok ? (uint32_t)max(__popc(c.S | ((c.near >> sh) & 31u)), 1) : 0u) << (4 * b);
+            gw |= (wild <= (uint32_t)c.yellow ? (mult >> sh) & 31u : 0u) << (4 * b);
         }
         gw <<= 16 * (g & 1);
         lo |= g < 2 ? gw : 0u;
