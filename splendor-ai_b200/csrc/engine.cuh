@@ -73,6 +73,7 @@ struct Tables {
     // as base-256 digit strings modulo 2^32
     uint32_t poly_pow[3][8];    // [lvl-1][n], n = 0..6
     uint32_t poly_inv[4];       // [lvl]
+    uint32_t recip[68];         // ceil(2^31 / d), d = 1..64 (small_div)
 };
 
 namespace detail {
@@ -225,6 +226,7 @@ __host__ __device__ constexpr Tables make_tables()
         for (int it = 0; it < 5; it++) x *= 2u - unit[l] * x;
         T.poly_inv[l] = x;
     }
+    for (int d = 1; d <= 64; d++) T.recip[d] = (uint32_t)(((1ull << 31) + (uint64_t)d - 1) / (uint64_t)d);
     return T;
 }
 
@@ -244,11 +246,6 @@ __device__ __forceinline__ uint32_t hsum6(uint32_t x)  // sum of the six fields 
 __device__ __forceinline__ uint32_t hsum6_small(uint32_t x)  // same, valid when the total is <= 31
 {
     return ((x * ONES6) >> 25) & 31u;
-}
-__device__ __forceinline__ uint32_t nibble_sum(uint32_t x)  // sum of the eight 4-bit fields (total <= 255)
-{
-    x = (x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu);
-    return (x * 0x01010101u) >> 24;
 }
 __device__ __forceinline__ uint32_t compress6(uint32_t h)  // guard bits (subset of H6) -> 6-bit field mask
 {
@@ -282,9 +279,13 @@ __device__ __forceinline__ int select_bit8(uint32_t m, int j)  // same for masks
     if (j >= (int)(m & 1u)) pos += 1;
     return pos;
 }
-__device__ __forceinline__ int small_div(int k, int d)  // floor(k/d) for 0 <= k < 8192, 1 <= d <= 64
+// floor(k/d) for 0 <= k < 8192, 1 <= d <= 64: ((2k+1) * ceil(2^31/d)) >> 32.  (2k+1)/(2d) is never an integer and lies at
+// least 1/(2d) below the next one, while the rounded-up reciprocal adds less than 2^14 / 2^32: exact (checked
+// exhaustively in tests/test_device_rules_hostsim.py).
+__device__ __forceinline__ int small_div(const Tables &T, int k, int d)
 {
-    return (int)__fdividef((float)k + 0.5f, (float)d);
+    SPL_CHECK(k >= 0 && k < 8192 && d >= 1 && d <= 64);
+    return (int)__umulhi(2u * (uint32_t)k + 1u, T.recip[d]);
 }
 __device__ __forceinline__ uint32_t occupied4(uint32_t dealt_word)  // 4-bit mask of non-empty slots (ids < 128, empty 0xFF)
 {
@@ -311,6 +312,25 @@ __device__ __forceinline__ uint4 philox_inline(uint64_t seed, uint64_t game, uin
 __device__ __noinline__ uint4 philox(uint64_t seed, uint64_t game, uint32_t index, uint32_t stream)
 {
     return philox_inline(seed, game, index, stream);
+}
+// Same generator with the key schedule precomputed (rk[2r] = key.x + r * 0x9E3779B9, rk[2r+1] = key.y + r * 0xBB67AE85).
+// The playout kernel passes the 20 words as kernel parameters, so each round is two wide multiplies and two
+// three-input XORs with a constant-bank operand: no key arithmetic, no key registers.
+__host__ __device__ inline void philox_round_keys(uint64_t seed, uint32_t *rk)
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+__device__ __forceinline__ uint4 philox_rk(const uint32_t *__restrict__ rk, uint64_t game, uint32_t index, uint32_t stream)
+{
+    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = index, c3 = stream;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r]; c1 = (uint32_t)p1;
+        c2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk[2 * r + 1]; c3 = (uint32_t)p0;
+    }
+    return make_uint4(c0, c1, c2, c3);
 }
 enum Stream { STREAM_ACTION = 0, STREAM_DECK0 = 1, STREAM_NOBLES = 4, STREAM_ENV = 5 };
 
@@ -349,6 +369,7 @@ __device__ __forceinline__ int seat_of(uint32_t meta) { return (meta >> 20) & 3;
 struct DeckSrc {
     const uint8_t *lists;  // explicit deck lists of THIS env (90 bytes) or nullptr
     uint64_t seed, game;
+    const uint32_t *rk;    // optional: the seed's Philox key schedule (philox_round_keys) in constant / parameter space
 };
 
 // BoardState.deal (splendor_model.py:95-99).  Counter-based decks: the d-th card dealt from a tier is the
@@ -373,24 +394,22 @@ __device__ __forceinline__ uint32_t deal(Env<P> &e, int tier, const DeckSrc &src
     else { lo = e.k[2] & 0xFFFFFu; size = 20; base = 70; }
     const int clo = __popc(lo), c = clo + __popc(hi);
     if (c == 0) return NONE8;
-    const uint32_t r = philox(src.seed, src.game, (uint32_t)(size - c), STREAM_DECK0 + tier).x;
-    int j = (int)__umulhi(r, (uint32_t)c), pos;
-    if (j < clo) {
-        pos = select_bit(lo, j);
-        if (tier == 0) e.k[0] &= ~(1u << pos);
-        else if (tier == 1) e.k[1] &= ~(1u << pos);
-        else e.k[2] &= ~(1u << pos);
-    } else {
-        pos = select_bit8(hi, j - clo);
-        e.k[2] &= ~(1u << (20 + pos));
-        pos += 32;
-    }
+    const uint32_t r = src.rk ? philox_rk(src.rk, src.game, (uint32_t)(size - c), STREAM_DECK0 + tier).x
+                              : philox(src.seed, src.game, (uint32_t)(size - c), STREAM_DECK0 + tier).x;
+    const int j = (int)__umulhi(r, (uint32_t)c);
+    // one select for both halves of the 40-bit first tier: no second code path for the eight high bits
+    const bool up = j >= clo;
+    const int pos = select_bit(up ? hi : lo, up ? j - clo : j) + (up ? 32 : 0);
+    const uint32_t bit = 1u << (pos & 31);
+    e.k[0] &= ~((tier == 0 && !up) ? bit : 0u);
+    e.k[1] &= ~(tier == 1 ? bit : 0u);
+    e.k[2] &= ~(tier == 2 ? bit : (up ? bit << 20 : 0u));
     return (uint32_t)(base + pos);
 }
 
 // SplendorState.__init__ (splendor_model.py:53-93) with Philox nobles and lazily drawn decks
 template <int P>
-__device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t game)
+__device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t game, const uint32_t *rk = nullptr)
 {
     const uint32_t n = P == 2 ? 4 : (P == 3 ? 5 : 7);
     e.bank = n * (ONES6 & ~(1u << YSH)) | (5u << YSH);
@@ -408,7 +427,7 @@ __device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t gam
         list = (list & ~(15u << (4 * i))) | ((uint32_t)vj << (4 * i));
     }
     e.meta = list | ((uint32_t)(P - 2) << 22);
-    DeckSrc src{nullptr, seed, game};
+    DeckSrc src{nullptr, seed, game, rk};
     e.d[0] = e.d[1] = e.d[2] = 0;
 #pragma unroll 1
     for (int i = 0; i < 12; i++) {  // one copy of deal() in the binary: the reset runs once per game, the step loop 90 times
@@ -453,7 +472,7 @@ __device__ __forceinline__ void make_ctx(const Env<P> &e, const Tables &T, Ctx &
     // noble_visit over the board list (:430-435) + which nobles are exactly one card of one colour away (:543-554)
     c.S = 0; c.near = 0;
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < P + 1; k++) {  // the board list never holds more than P + 1 nobles (:90-93)
         const uint32_t d = satsub6(T.noble[(e.meta >> (4 * k)) & 15u], c.cards);
         c.S |= (d == 0 ? 1u : 0u) << k;
         c.near |= ((d & (d - 1)) == 0 ? d & ONES6 : 0u) << k;  // exactly one gem of one colour short (branch-free)
@@ -476,7 +495,7 @@ struct FamilyCounts {
     int res, same, diff, bres, bav;  // actions per family (noble multiplicity included)
     uint32_t grp[9];                 // return variants per collect group, one byte each, in ALL_ACTIONS order:
                                      // bytes 0..4 the collect_same colours, bytes 8..32 the collect_diff combos 0..24
-    uint32_t buy_lo, buy_hi;         // buy actions per card, 4 bits each: board slots 0..7 | slots 8..11 + reserved 0..2
+    uint32_t buy[4];                 // buy actions per card, one byte each, in ALL_ACTIONS order: the 3 reserved cards | board rows 0, 1, 2
 };
 
 __device__ __forceinline__ int reserve_variants(const Ctx &c)
@@ -607,16 +626,18 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
         mult |= (uint32_t)max(__popc(c.S | ((c.near >> sh) & 31u)), 1) << sh;
     }
     mult &= ~((((c.cards + 9u * ONES6) & H6) >> 4) * 31u);
-    uint32_t lo = 0, hi = 0;
+    // wilds needed = sum of max(cost - cards - gems, 0) <= 14; x * (ONES6 << 2) leaves that sum in the top five bits (what
+    // would lie above falls off), so "sum <= yellow" is one compare of the product against ((yellow + 1) << 27) - 1
+    const uint32_t wild_max = (((uint32_t)c.yellow + 1u) << 27) - 1u;
+    uint32_t bw[4] = {0u, 0u, 0u, 0u};
     if (!COMPACT) {
 #pragma unroll
     for (int s = 0; s < 15; s++) {
         const uint32_t w = s < 12 ? e.d[s >> 2] : c.resv;
         const uint2 cw = T.card[(w >> (8 * (s & 3))) & 127u];
         const uint32_t sh = cw.y & 31u;
-        const uint32_t wild = hsum6_small(satsub6(cw.x, eff));   // max(cost - cards - gems, 0) summed = wilds needed
-        const uint32_t cnt = wild <= (uint32_t)c.yellow ? (mult >> sh) & 31u : 0u;
-        if (s < 8) lo |= cnt << (4 * s); else hi |= cnt << (4 * (s - 8));
+        const uint32_t cnt = satsub6(cw.x, eff) * (ONES6 << 2) <= wild_max ? (mult >> sh) & 31u : 0u;
+        bw[s < 12 ? 1 + (s >> 2) : 0] += cnt << (8 * (s & 3));
     }
     } else {
     // four groups of four slots (three board rows, then the reserved list whose 4th byte is forced empty): rolled to keep
@@ -630,17 +651,14 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
         for (int b = 0; b < 4; b++) {
             const uint2 cw = T.card[(w >> (8 * b)) & 127u];
             const uint32_t sh = cw.y & 31u;
-            const uint32_t wild = hsum6_small(satsub6(cw.x, eff));   // max(cost - cards - gems, 0) summed = wilds needed
-            gw |= (wild <= (uint32_t)c.yellow ? (mult >> sh) & 31u : 0u) << (4 * b);
+            gw += (satsub6(cw.x, eff) * (ONES6 << 2) <= wild_max ? (mult >> sh) & 31u : 0u) << (8 * b);
         }
-        gw <<= 16 * (g & 1);
-        lo |= g < 2 ? gw : 0u;
-        hi |= g < 2 ? 0u : gw;
+        if (g == 0) bw[1] = gw; else if (g == 1) bw[2] = gw; else if (g == 2) bw[3] = gw; else bw[0] = gw;
     }
     }
-    f.buy_lo = lo; f.buy_hi = hi;
-    f.bav = (int)(nibble_sum(lo) + nibble_sum(hi & 0xFFFFu));
-    f.bres = (int)nibble_sum(hi >> 16);
+    f.buy[0] = bw[0]; f.buy[1] = bw[1]; f.buy[2] = bw[2]; f.buy[3] = bw[3];
+    f.bres = (int)((bw[0] * 0x01010101u) >> 24);
+    f.bav = (int)(((bw[1] + bw[2] + bw[3]) * 0x01010101u) >> 24);  // bytes <= 5, 6 nobles slots at most
     return f.res + f.same + f.diff + f.bres + f.bav;
 }
 
@@ -659,7 +677,7 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
     }
     if (k < f.res) {  // reserve: index 6 + p*42 + n*7 + v
         const int nv = reserve_variants(c), per = c.nS * nv;
-        const int q = small_div(k, per), rem = k - q * per, ni = small_div(rem, nv), vi = rem - ni * nv;
+        const int q = small_div(T, k, per), rem = k - q * per, ni = small_div(T, rem, nv), vi = rem - ni * nv;
         ch.type = T_RESERVE;
         ch.slot = select_bit(c.occ, q);
         ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
@@ -682,7 +700,7 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
         // variants * nS consecutive legal actions.  Find the group of action k in two prefix-sum steps - the word, then
         // the byte inside it (a multiply by 0x01010101 turns four counts into their four running sums) - then the noble
         // slot and the vi-th payable return variant of the group's table row.
-        const uint32_t q = (uint32_t)small_div(k, c.nS);
+        const uint32_t q = (uint32_t)small_div(T, k, c.nS);
         uint32_t W = f.grp[0], before = 0, run = 0;
         int wi = 0;
 #pragma unroll
@@ -717,7 +735,7 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
             ch.type = T_DIFF; ch.slot = ci;
             ch.C = T.combo_c[ci];
         }
-        const int ni = small_div(k, nv), vi = k - ni * nv;
+        const int ni = small_div(T, k, nv), vi = k - ni * nv;
         SPL_CHECK(nv >= 1 && nv == __popc(vbits) && vi >= 0 && vi < nv && ni < c.nS);
         const int v = select_bit(vbits, vi);  // the vi-th payable return variant, ascending
         SPL_CHECK(v < V);
@@ -728,19 +746,24 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
     }
     k -= f.same + f.diff;
     // buys: reserved cards first (3420 + r*6 + n), then the board (3438 + p*6 + n); per-card counts come packed from count_legal
-    int s = 12;
+    // the card of action k by the same two prefix-sum steps as the collect groups (word, then byte); what is left of k
+    // is the noble choice
+    int s;
     {
-        uint32_t w = f.buy_hi >> 16;
-        int i = 0;
-        for (; i < 15; i++) {
-            if (i == 3) w = f.buy_lo;
-            if (i == 11) w = f.buy_hi;
-            const int cnt = (int)(w & 15u);
-            if (k < cnt) break;
-            k -= cnt;
-            w >>= 4;
+        uint32_t W = f.buy[0], before = 0, run = 0;
+        int wi = 0;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            if (w > 0 && (uint32_t)k >= run) { W = f.buy[w]; before = run; wi = w; }
+            run += (f.buy[w] * 0x01010101u) >> 24;
         }
-        s = i < 3 ? 12 + i : i - 3;
+        SPL_CHECK((uint32_t)k < run);
+        const uint32_t sums = W * 0x01010101u;
+        const uint32_t ahead = ((((uint32_t)k - before) * 0x01010101u | 0x80808080u) - sums) & 0x80808080u;
+        const int b = __popc(ahead);
+        k -= (int)(before + (((sums << 8) >> (8 * b)) & 255u));
+        s = wi == 0 ? 12 + b : 4 * (wi - 1) + b;
+        SPL_CHECK(b < 4 && s < 15 && k >= 0 && k < 6);
     }
     {
         const uint32_t w = s < 4 ? e.d[0] : (s < 8 ? e.d[1] : (s < 12 ? e.d[2] : c.resv));

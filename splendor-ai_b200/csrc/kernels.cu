@@ -106,6 +106,7 @@ struct PlayoutArgs {
     unsigned long long *counters;
     int16_t *trace;
     int trace_len;
+    uint32_t rk[20];        // Philox key schedule of `seed` (filled by launch_playout)
 };
 
 template <int P>
@@ -124,7 +125,7 @@ __device__ __forceinline__ uint32_t turns_total(const Env<P> &e)
 // different phase - reset / finalize ran one lane at a time and the instruction cache thrashed - and was 25-40 % slower
 // on large sweeps (profiles/r1_playout_ncu.md).
 template <int P, bool FRESH, bool COMPACT>
-__global__ void __launch_bounds__(BLOCK, COMPACT ? 7 : 5) playout_kernel(const PlayoutArgs a)  // 72 / 96 registers
+__global__ void __launch_bounds__(BLOCK, COMPACT ? 7 : 5) playout_kernel(const __grid_constant__ PlayoutArgs a)  // 72 / 96 registers
 {
     __shared__ Tables sT;
     __shared__ unsigned long long sctr[16];
@@ -136,8 +137,8 @@ __global__ void __launch_bounds__(BLOCK, COMPACT ? 7 : 5) playout_kernel(const P
     Env<P> e;
     int t = 0, kind = SPL_END_NONE;
     if (live) {
-        DeckSrc src{nullptr, a.seed, (!FRESH && a.game_ids) ? a.game_ids[g] : a.first_game + (uint64_t)g};
-        if (FRESH) reset_env(e, a.seed, src.game);
+        DeckSrc src{nullptr, a.seed, (!FRESH && a.game_ids) ? a.game_ids[g] : a.first_game + (uint64_t)g, a.rk};
+        if (FRESH) reset_env(e, a.seed, src.game, a.rk);
         else {
             load_env(e, a.state, a.n_games, g);
             src.lists = a.decks ? a.decks + g * SPL_DECK_BYTES : nullptr;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(BLOCK, COMPACT ? 7 : 5) playout_kernel(const P
             Ctx c;
             FamilyCounts f;
             Choice ch;
-            const uint32_t r = philox_inline(a.seed, src.game, (uint32_t)t, STREAM_ACTION).x;
+            const uint32_t r = philox_rk(a.rk, src.game, (uint32_t)t, STREAM_ACTION).x;
             make_ctx(e, sT, c);
             const int total = count_legal<P, COMPACT>(e, sT, c, f);
             select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
@@ -918,8 +919,10 @@ int spl_observe(const void *state, const int8_t *seat, float *obs, int64_t N, in
     return launch_observe(state, seat, obs, N, P, (cudaStream_t)stream);
 }
 
-static int launch_playout(bool fresh, const PlayoutArgs &a, int P, cudaStream_t stream)
+static int launch_playout(bool fresh, const PlayoutArgs &args, int P, cudaStream_t stream)
 {
+    PlayoutArgs a = args;
+    philox_round_keys(a.seed, a.rk);
     if (a.max_steps < 1 || a.max_steps > 4096 || a.trace_len < 0) return SPL_E_RANGE;
     if (a.trace && a.trace_len > 0)
         CK(cudaMemsetAsync(a.trace, 0xFF, (size_t)a.trace_len * (size_t)a.n_games * sizeof(int16_t), stream));

@@ -206,5 +206,14 @@ int sim_playout(uint32_t *w, int fresh, const uint8_t *lists, uint64_t seed, uin
 { DISPATCH(P, return t_playout<PP>(w, fresh != 0, lists, seed, game, flags, max_steps, trace, trace_len, score2, kind)); return -1; }
 void sim_philox(uint64_t seed, uint64_t game, uint32_t index, uint32_t stream, uint32_t *out)
 { uint4 r = philox(seed, game, index, stream); out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w; }
+void sim_philox_rk(uint64_t seed, uint64_t game, uint32_t index, uint32_t stream, uint32_t *out)
+{ uint32_t rk[20]; philox_round_keys(seed, rk); uint4 r = philox_rk(rk, game, index, stream); out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w; }
 int sim_tables_bytes(void) { return (int)sizeof(Tables); }
+int sim_small_div_mismatches(void)  // the whole documented domain of small_div against integer division
+{
+    int bad = 0;
+    for (int d = 1; d <= 64; d++)
+        for (int k = 0; k < 8192; k++) bad += small_div(T, k, d) != k / d;
+    return bad;
+}
 }

@@ -32,6 +32,7 @@ def lib():
         _lib.sim_playout.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_int,
                                      C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         _lib.sim_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
+        _lib.sim_philox_rk.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
     return _lib
 
 

@@ -107,8 +107,14 @@ def test_philox_matches_oracle(oracle):
     for seed, game, idx, stream in [(0, 0, 0, 0), (1234, 5, 17, 2), (2**63 + 11, 2**40 + 3, 4000000000, 5)]:
         S.lib().sim_philox(seed, game, idx, stream, out.ctypes.data)
         assert np.array_equal(out, oracle.philox(seed, game, idx, stream))
+        S.lib().sim_philox_rk(seed, game, idx, stream, out.ctypes.data)  # the precomputed-key-schedule form of the playout kernel
+        assert np.array_equal(out, oracle.philox(seed, game, idx, stream))
     # known-answer vectors of Philox4x32-10 from the Random123 distribution (kat_vectors)
     S.lib().sim_philox(0, 0, 0, 0, out.ctypes.data)
     assert [hex(x) for x in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
     S.lib().sim_philox(0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, out.ctypes.data)
     assert [hex(x) for x in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+def test_small_div_is_exact_on_its_domain():
+    assert S.lib().sim_small_div_mismatches() == 0
