@@ -74,6 +74,8 @@ struct Tables {
     uint32_t poly_pow[3][8];    // [lvl-1][n], n = 0..6
     uint32_t poly_inv[4];       // [lvl]
     uint32_t recip[68];         // ceil(2^31 / d), d = 1..64 (small_div)
+    uint2 buyrow[128];          // card[] with the guard bits already set in the cost (.x | H6): one instruction less per
+                                // candidate in count_legal's affordability test
 };
 
 namespace detail {
@@ -226,6 +228,7 @@ __host__ __device__ constexpr Tables make_tables()
         for (int it = 0; it < 5; it++) x *= 2u - unit[l] * x;
         T.poly_inv[l] = x;
     }
+    for (int i = 0; i < 128; i++) T.buyrow[i] = uint2{T.card[i].x | H6, T.card[i].y};
     for (int d = 1; d <= 64; d++) T.recip[d] = (uint32_t)(((1ull << 31) + (uint64_t)d - 1) / (uint64_t)d);
     return T;
 }
@@ -234,6 +237,13 @@ __host__ __device__ constexpr Tables make_tables()
 __device__ __forceinline__ uint32_t satsub6(uint32_t a, uint32_t b)  // per field max(a-b,0); fields < 16
 {
     uint32_t d = (a | H6) - b;
+    uint32_t m = d & H6;
+    m -= m >> 4;
+    return d & m;
+}
+__device__ __forceinline__ uint32_t satsub6g(uint32_t ag, uint32_t b)  // satsub6 for an `a` that already carries the guard bits
+{
+    uint32_t d = ag - b;
     uint32_t m = d & H6;
     m -= m >> 4;
     return d & m;
@@ -608,9 +618,7 @@ __device__ __forceinline__ void collect_groups(const Tables &T, const Ctx &c, Fa
     f.diff = (int)(((dsum * 0x01010101u) >> 24) * (uint32_t)c.nS);
 }
 
-// COMPACT = smaller code (rolled loops) for launches where warps are spread over reset / step / finalize and the
-// instruction cache is the bottleneck (>= 2^20 games); the unrolled form is ~3 % faster for small launches.
-template <int P, bool COMPACT = false>
+template <int P>
 __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, const Ctx &c, FamilyCounts &f)
 {
     f.res = c.n_resv < 3 ? __popc(c.occ) * c.nS * reserve_variants(c) : 0;
@@ -630,31 +638,13 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
     // would lie above falls off), so "sum <= yellow" is one compare of the product against ((yellow + 1) << 27) - 1
     const uint32_t wild_max = (((uint32_t)c.yellow + 1u) << 27) - 1u;
     uint32_t bw[4] = {0u, 0u, 0u, 0u};
-    if (!COMPACT) {
 #pragma unroll
     for (int s = 0; s < 15; s++) {
         const uint32_t w = s < 12 ? e.d[s >> 2] : c.resv;
-        const uint2 cw = T.card[(w >> (8 * (s & 3))) & 127u];
+        const uint2 cw = T.buyrow[(w >> (8 * (s & 3))) & 127u];
         const uint32_t sh = cw.y & 31u;
-        const uint32_t cnt = satsub6(cw.x, eff) * (ONES6 << 2) <= wild_max ? (mult >> sh) & 31u : 0u;
+        const uint32_t cnt = satsub6g(cw.x, eff) * (ONES6 << 2) <= wild_max ? (mult >> sh) & 31u : 0u;
         bw[s < 12 ? 1 + (s >> 2) : 0] += cnt << (8 * (s & 3));
-    }
-    } else {
-    // four groups of four slots (three board rows, then the reserved list whose 4th byte is forced empty): rolled to keep
-    // the step loop inside the instruction cache (profiles/r1h: no_instruction stalls when warps are spread over
-    // reset / step / finalize code)
-#pragma unroll 1
-    for (int g = 0; g < 4; g++) {
-        const uint32_t w = g == 0 ? e.d[0] : (g == 1 ? e.d[1] : (g == 2 ? e.d[2] : (c.resv | 0xFF000000u)));
-        uint32_t gw = 0;
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const uint2 cw = T.card[(w >> (8 * b)) & 127u];
-            const uint32_t sh = cw.y & 31u;
-            gw += (satsub6(cw.x, eff) * (ONES6 << 2) <= wild_max ? (mult >> sh) & 31u : 0u) << (8 * b);
-        }
-        if (g == 0) bw[1] = gw; else if (g == 1) bw[2] = gw; else if (g == 2) bw[3] = gw; else bw[0] = gw;
-    }
     }
     f.buy[0] = bw[0]; f.buy[1] = bw[1]; f.buy[2] = bw[2]; f.buy[3] = bw[3];
     f.bres = (int)((bw[0] * 0x01010101u) >> 24);
@@ -669,18 +659,23 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
 {
     ch.C = 0; ch.R = 0; ch.info = 0; ch.slot = 0;
     SPL_CHECK(k >= 0 && k < (total ? total : c.nS));
-    if (total == 0) {  // pass (:570-574)
+    // Every family ends the same way - pick the pj-th set bit of a mask (board slot / return variant), pick the ni-th
+    // noble of a set, index = base + n * nmul + pos * pmul - so the families only prepare those operands and the picks
+    // run ONCE for the whole warp after the branches have rejoined (a warp almost always holds lanes of every family;
+    // code inside the branches is paid once per family, code after them once).
+    uint32_t pm = 1u, Sb = c.S;
+    int pj = 0, ni = 0, base = 0, nmul = 1, pmul = 0;
+    const uint32_t *row = T.ret_same;  // collect families: returned gems of variant `pos`; others: not read
+    if (total == 0) {  // pass (:570-574): index = noble slot
         ch.type = T_PASS;
-        ch.n = c.S ? select_bit8(c.S, k) + 1 : 0;
-        ch.idx = ch.n;
-        return;
-    }
-    if (k < f.res) {  // reserve: index 6 + p*42 + n*7 + v
+        ni = k;
+    } else if (k < f.res) {  // reserve: index 6 + p*42 + n*7 + v
         const int nv = reserve_variants(c), per = c.nS * nv;
-        const int q = small_div(T, k, per), rem = k - q * per, ni = small_div(T, rem, nv), vi = rem - ni * nv;
+        const int q = small_div(T, k, per), rem = k - q * per;
+        ni = small_div(T, rem, nv);
+        const int vi = rem - ni * nv;
         ch.type = T_RESERVE;
-        ch.slot = select_bit(c.occ, q);
-        ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
+        pm = c.occ; pj = q;
         int v = 0;
         if (c.bank_yellow) {
             v = 1; ch.C = 1u << YSH;
@@ -690,16 +685,14 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
                 ch.R = 1u << (5 * fl);
             }
         }
-        ch.idx = BASE_RESERVE + ch.slot * 42 + ch.n * 7 + v;
-        return;
-    }
-    k -= f.res;
-    if (k < f.same + f.diff) {
+        base = BASE_RESERVE + v; nmul = 7; pmul = 42;
+    } else if (k - f.res < f.same + f.diff) {
         // collect_same (510 + c*126 + n*21 + v) and collect_diff (combo_base + n*V + v).  The 30 groups (colours, then
         // colour combinations) lie in index order in f.grp, one byte of return-variant count each; a group holds
         // variants * nS consecutive legal actions.  Find the group of action k in two prefix-sum steps - the word, then
         // the byte inside it (a multiply by 0x01010101 turns four counts into their four running sums) - then the noble
         // slot and the vi-th payable return variant of the group's table row.
+        k -= f.res;
         const uint32_t q = (uint32_t)small_div(T, k, c.nS);
         uint32_t W = f.grp[0], before = 0, run = 0;
         int wi = 0;
@@ -716,40 +709,30 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
         before += ((sums << 8) >> (8 * b)) & 255u;
         const int nv = (int)((W >> (8 * b)) & 255u);
         k -= (int)before * c.nS;
-        const uint32_t *row;
-        int base, V;
-        uint32_t vbits;
         if (g < 8) {
             const int col = g, e2 = c.hold - 8;
             row = T.ret_same + col * 21;
-            base = BASE_SAME + col * 126; V = 21;
-            vbits = same_variant_bits(T, c, col, e2);
+            base = BASE_SAME + col * 126; nmul = 21;
+            pm = same_variant_bits(T, c, col, e2);
             ch.type = T_SAME; ch.slot = col;
             ch.C = 2u << (5 * field_of_normal(col));
         } else {
             const int ci = g - 8, L = combo_len(ci);
-            V = L == 1 ? 6 : (L == 2 ? 15 : 20);
+            nmul = L == 1 ? 6 : (L == 2 ? 15 : 20);
             row = T.ret_diff + T.combo_off[ci];
             base = T.combo_base[ci];
-            vbits = diff_variant_bits(T, c, ci, L, c.hold + L - 10);
+            pm = diff_variant_bits(T, c, ci, L, c.hold + L - 10);
             ch.type = T_DIFF; ch.slot = ci;
             ch.C = T.combo_c[ci];
         }
-        const int ni = small_div(T, k, nv), vi = k - ni * nv;
-        SPL_CHECK(nv >= 1 && nv == __popc(vbits) && vi >= 0 && vi < nv && ni < c.nS);
-        const int v = select_bit(vbits, vi);  // the vi-th payable return variant, ascending
-        SPL_CHECK(v < V);
-        ch.n = c.S ? select_bit8(c.S, ni) + 1 : 0;
-        ch.R = row[v];
-        ch.idx = base + ch.n * V + v;
-        return;
-    }
-    k -= f.same + f.diff;
-    // buys: reserved cards first (3420 + r*6 + n), then the board (3438 + p*6 + n); per-card counts come packed from count_legal
-    // the card of action k by the same two prefix-sum steps as the collect groups (word, then byte); what is left of k
-    // is the noble choice
-    int s;
-    {
+        ni = small_div(T, k, nv);
+        pj = k - ni * nv;  // the pj-th payable return variant, ascending
+        pmul = 1;
+        SPL_CHECK(nv >= 1 && nv == __popc(pm) && pj >= 0 && pj < nv && ni < c.nS);
+    } else {
+        // buys: reserved cards first (3420 + r*6 + n), then the board (3438 + p*6 + n).  The card of action k by the same
+        // two prefix-sum steps as the collect groups (word, then byte); what is left of k is the noble choice
+        k -= f.res + f.same + f.diff;
         uint32_t W = f.buy[0], before = 0, run = 0;
         int wi = 0;
 #pragma unroll
@@ -761,21 +744,25 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
         const uint32_t sums = W * 0x01010101u;
         const uint32_t ahead = ((((uint32_t)k - before) * 0x01010101u | 0x80808080u) - sums) & 0x80808080u;
         const int b = __popc(ahead);
-        k -= (int)(before + (((sums << 8) >> (8 * b)) & 255u));
-        s = wi == 0 ? 12 + b : 4 * (wi - 1) + b;
-        SPL_CHECK(b < 4 && s < 15 && k >= 0 && k < 6);
-    }
-    {
+        ni = k - (int)(before + (((sums << 8) >> (8 * b)) & 255u));
+        const int s = wi == 0 ? 12 + b : 4 * (wi - 1) + b;
+        SPL_CHECK(b < 4 && s < 15 && ni >= 0 && ni < 6);
         const uint32_t w = s < 4 ? e.d[0] : (s < 8 ? e.d[1] : (s < 12 ? e.d[2] : c.resv));
         const uint2 cw = T.card[byte_of(w, s & 3) & 127u];
-        const uint32_t Sb = c.S | ((c.near >> (cw.y & 31u)) & 31u);
+        Sb = c.S | ((c.near >> (cw.y & 31u)) & 31u);
         can_buy(c, cw, ch.R);
         ch.type = s < 12 ? T_BUY_AVAILABLE : T_BUY_RESERVE;
         ch.slot = s < 12 ? s : s - 12;
-        ch.n = Sb ? select_bit8(Sb, k) + 1 : 0;
         ch.info = cw.y;
-        ch.idx = (s < 12 ? BASE_BUY_AVAILABLE + s * 6 : BASE_BUY_RESERVE + (s - 12) * 6) + ch.n;
+        base = s < 12 ? BASE_BUY_AVAILABLE + s * 6 : BASE_BUY_RESERVE + (s - 12) * 6;
     }
+    // ---- the shared tail
+    SPL_CHECK(pj >= 0 && pj < __popc(pm));
+    const int pos = select_bit(pm, pj);
+    ch.n = Sb ? select_bit8(Sb, ni) + 1 : 0;
+    ch.idx = base + ch.n * nmul + pos * pmul;
+    if (ch.type == T_RESERVE) ch.slot = pos;
+    if (pmul == 1) { SPL_CHECK(pos < nmul); ch.R = row[pos]; }
 }
 
 // Is ALL_ACTIONS[idx] legal for the seat to move?  Decodes it into ch either way (build_action, gym/envs/utils.py:43-145).

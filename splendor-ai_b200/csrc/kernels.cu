@@ -29,6 +29,9 @@ __device__ const uint32_t g_log1p_bits[32] = SPL_LOG1P_BITS;
 
 constexpr int BLOCK = 128;
 constexpr int PLAYOUT_BLOCK = 128;  // default threads per block of the playout kernel
+#ifndef SPL_PLAYOUT_MINBLOCKS
+#define SPL_PLAYOUT_MINBLOCKS 5  // resident 128-thread blocks per SM the playout kernel is compiled for (register cap)
+#endif
 
 __device__ __forceinline__ void stage_tables(Tables &sT)
 {
@@ -124,8 +127,8 @@ __device__ __forceinline__ uint32_t turns_total(const Env<P> &e)
 // score together).  An earlier persistent form (lanes drew their next game themselves) left each lane of a warp in a
 // different phase - reset / finalize ran one lane at a time and the instruction cache thrashed - and was 25-40 % slower
 // on large sweeps (profiles/r1_playout_ncu.md).
-template <int P, bool FRESH, bool COMPACT>
-__global__ void __launch_bounds__(BLOCK, COMPACT ? 7 : 5) playout_kernel(const __grid_constant__ PlayoutArgs a)  // 72 / 96 registers
+template <int P, bool FRESH>
+__global__ void __launch_bounds__(BLOCK, SPL_PLAYOUT_MINBLOCKS) playout_kernel(const __grid_constant__ PlayoutArgs a)  // 92 registers
 {
     __shared__ Tables sT;
     __shared__ unsigned long long sctr[16];
@@ -154,9 +157,9 @@ __global__ void __launch_bounds__(BLOCK, COMPACT ? 7 : 5) playout_kernel(const _
             Choice ch;
             const uint32_t r = philox_rk(a.rk, src.game, (uint32_t)t, STREAM_ACTION).x;
             make_ctx(e, sT, c);
-            const int total = count_legal<P, COMPACT>(e, sT, c, f);
+            const int total = count_legal(e, sT, c, f);
             select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
-            if (a.trace && t < a.trace_len) a.trace[(int64_t)t * a.n_games + g] = (int16_t)ch.idx;
+            if (__builtin_expect(t < a.trace_len, 0)) a.trace[(int64_t)t * a.n_games + g] = (int16_t)ch.idx;  // trace_len is 0 without a trace
             apply_action(e, ch, src);
             t++;
         }
@@ -924,6 +927,7 @@ static int launch_playout(bool fresh, const PlayoutArgs &args, int P, cudaStream
     PlayoutArgs a = args;
     philox_round_keys(a.seed, a.rk);
     if (a.max_steps < 1 || a.max_steps > 4096 || a.trace_len < 0) return SPL_E_RANGE;
+    if (!a.trace) a.trace_len = 0;  // the kernel tests trace_len only
     if (a.trace && a.trace_len > 0)
         CK(cudaMemsetAsync(a.trace, 0xFF, (size_t)a.trace_len * (size_t)a.n_games * sizeof(int16_t), stream));
     static int blk = 0;
@@ -932,16 +936,12 @@ static int launch_playout(bool fresh, const PlayoutArgs &args, int P, cudaStream
         blk = s ? atoi(s) : PLAYOUT_BLOCK;
         if (blk != 32 && blk != 64 && blk != 96 && blk != 128) blk = PLAYOUT_BLOCK;
     }
-    // two instantiations: the register-lean one (rolled buy loop, 72 registers: 7 blocks per SM instead of 6) wins as soon
-    // as the launch fills the GPU more than once; below that the faster straight-line code wins
-    static int force = -1;
-    if (force < 0) { const char *s = getenv("SPL_PLAYOUT_COMPACT"); force = s ? (atoi(s) ? 1 : 0) : 2; }
+    // One instantiation per player count.  Up to r1n a second, register-lean one (rolled buy loop, 72 registers, 7 blocks
+    // per SM) won on launches of >= 2^20 games; after the r1o-r1q rewrite of the step it spills and is 6 % slower there
+    // (profiles/r1q_playout.md), so it was removed.
     const unsigned grid = (unsigned)((a.n_games + blk - 1) / blk);
-    const bool compact = force == 2 ? (int64_t)grid * blk > (int64_t)sm_count() * 640 : force == 1;
-    if (fresh && compact) { DISPATCH_P(P, playout_kernel<PP, true, true><<<grid, blk, 0, stream>>>(a)); }
-    else if (fresh) { DISPATCH_P(P, playout_kernel<PP, true, false><<<grid, blk, 0, stream>>>(a)); }
-    else if (compact) { DISPATCH_P(P, playout_kernel<PP, false, true><<<grid, blk, 0, stream>>>(a)); }
-    else { DISPATCH_P(P, playout_kernel<PP, false, false><<<grid, blk, 0, stream>>>(a)); }
+    if (fresh) { DISPATCH_P(P, playout_kernel<PP, true><<<grid, blk, 0, stream>>>(a)); }
+    else { DISPATCH_P(P, playout_kernel<PP, false><<<grid, blk, 0, stream>>>(a)); }
     CK(cudaGetLastError());
     return SPL_OK;
 }
