@@ -74,8 +74,8 @@ struct Tables {
     uint32_t poly_pow[3][8];    // [lvl-1][n], n = 0..6
     uint32_t poly_inv[4];       // [lvl]
     uint32_t recip[68];         // ceil(2^31 / d), d = 1..64 (small_div)
-    uint2 buyrow[128];          // card[] with the guard bits already set in the cost (.x | H6): one instruction less per
-                                // candidate in count_legal's affordability test
+    uint2 buyrow[256];          // card[] for count_legal's affordability test: guard bits already set in the cost (.x | H6),
+                                // and indexed by the raw slot byte (0xFF = empty slot -> filler), so no masking of the id
 };
 
 namespace detail {
@@ -228,7 +228,7 @@ __host__ __device__ constexpr Tables make_tables()
         for (int it = 0; it < 5; it++) x *= 2u - unit[l] * x;
         T.poly_inv[l] = x;
     }
-    for (int i = 0; i < 128; i++) T.buyrow[i] = uint2{T.card[i].x | H6, T.card[i].y};
+    for (int i = 0; i < 256; i++) T.buyrow[i] = uint2{T.card[i & 127].x | H6, T.card[i & 127].y & 31u};  // .y: the colour's bit offset only
     for (int d = 1; d <= 64; d++) T.recip[d] = (uint32_t)(((1ull << 31) + (uint64_t)d - 1) / (uint64_t)d);
     return T;
 }
@@ -554,7 +554,7 @@ __device__ __forceinline__ bool can_buy(const Ctx &c, uint2 cw, uint32_t &pay)
 // So with G = the product over all six colours, a collect group that takes the colours {a,b,c} has
 //     variants = digit_e( G * I_a * I_b * I_c ),   e = gems over the limit of 10 (digit 0 is 1: "return nothing"),
 // and an unavailable colour (bank empty, or < 4 for collect_same) is folded in as I = 0, which zeroes the whole group.
-// 38 multiplies and 21 byte permutes give all 30 groups of a decision at once, packed one byte per group in
+// 45 multiplies and 23 byte permutes give all 30 groups of a decision at once, packed one byte per group in
 // ALL_ACTIONS order; select_legal finds the k-th action with two SWAR prefix-sum steps instead of walking the groups.
 __device__ __forceinline__ uint32_t pick2(uint32_t x, uint32_t y, uint32_t sel) { return __byte_perm(x, y, sel); }
 __device__ __forceinline__ uint32_t pack4(uint32_t xy, uint32_t zw) { return __byte_perm(xy, zw, 0x5410u); }
@@ -641,8 +641,8 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
 #pragma unroll
     for (int s = 0; s < 15; s++) {
         const uint32_t w = s < 12 ? e.d[s >> 2] : c.resv;
-        const uint2 cw = T.buyrow[(w >> (8 * (s & 3))) & 127u];
-        const uint32_t sh = cw.y & 31u;
+        const uint2 cw = T.buyrow[__byte_perm(w, 0u, 0x4440u + (s & 3))];  // byte s & 3 of w
+        const uint32_t sh = cw.y;
         const uint32_t cnt = satsub6g(cw.x, eff) * (ONES6 << 2) <= wild_max ? (mult >> sh) & 31u : 0u;
         bw[s < 12 ? 1 + (s >> 2) : 0] += cnt << (8 * (s & 3));
     }

@@ -1019,7 +1019,7 @@ int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t 
     std::lock_guard<std::mutex> lock(g_stage_mu);
     // The batch is cut into chunks that travel on separate internal streams: the H2D copy of chunk k+1 and the D2H copy
     // of chunk k-1 overlap the kernels of chunk k (and the chunk kernels, latency-bound at this size, overlap each other).
-    constexpr int MAX_CHUNKS = 4;
+    constexpr int MAX_CHUNKS = 8, HOST_CHUNKS_DEFAULT = 4;
     static cudaStream_t side[MAX_CHUNKS] = {};
     static cudaEvent_t ev_start = nullptr, ev_done[MAX_CHUNKS] = {};
     if (!ev_start) {
@@ -1029,7 +1029,13 @@ int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t 
             CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
         }
     }
-    const int n_chunks = N >= 16384 ? MAX_CHUNKS : 1;
+    static int want_chunks = 0;
+    if (!want_chunks) {  // SPL_HOST_CHUNKS: 1..8, a tuning knob (profiles/r1q_playout.md)
+        const char *s = getenv("SPL_HOST_CHUNKS");
+        want_chunks = s ? atoi(s) : HOST_CHUNKS_DEFAULT;
+        if (want_chunks < 1 || want_chunks > MAX_CHUNKS) want_chunks = HOST_CHUNKS_DEFAULT;
+    }
+    const int n_chunks = N >= 16384 ? want_chunks : 1;
     const int64_t per = (N + n_chunks - 1) / n_chunks;
     const size_t W = (size_t)(8 + 4 * P) * 4;
     const size_t o_state = 0, o_decks = o_state + align256((size_t)N * W) + 256 * MAX_CHUNKS,
