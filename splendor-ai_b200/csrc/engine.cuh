@@ -385,10 +385,10 @@ struct DeckSrc {
 // BoardState.deal (splendor_model.py:95-99).  Counter-based decks: the d-th card dealt from a tier is the
 // floor(u*c)-th smallest id still in the deck (c cards left, u = Philox word of (seed, game, d, tier)) - a lazy
 // Fisher-Yates draw whose order is a function of (seed, game) only, never of the actions played.
-template <int P>
+template <int P, bool LISTS = false>  // LISTS: the caller guarantees src.lists (no counter-based code is generated)
 __device__ __forceinline__ uint32_t deal(Env<P> &e, int tier, const DeckSrc &src)
 {
-    if (src.lists) {  // explicit lists: pop from the end
+    if (LISTS || src.lists) {  // explicit lists: pop from the end
         uint32_t cnt = byte_of(e.k[0], tier);
         if (cnt == 0) return NONE8;
         cnt--;
@@ -417,14 +417,11 @@ __device__ __forceinline__ uint32_t deal(Env<P> &e, int tier, const DeckSrc &src
     return (uint32_t)(base + pos);
 }
 
-// SplendorState.__init__ (splendor_model.py:53-93) with Philox nobles and lazily drawn decks
+// random.sample(NOBLES, P+1): partial Fisher-Yates over the 10 ids held as nibbles of a 64-bit word; returns the board's
+// noble list (5 nibbles, 0xF = none)
 template <int P>
-__device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t game, const uint32_t *rk = nullptr)
+__device__ __forceinline__ uint32_t sample_nobles(uint64_t seed, uint64_t game)
 {
-    const uint32_t n = P == 2 ? 4 : (P == 3 ? 5 : 7);
-    e.bank = n * (ONES6 & ~(1u << YSH)) | (5u << YSH);
-    e.k[0] = 0xFFFFFFFFu; e.k[1] = 0x3FFFFFFFu; e.k[2] = 0x0FFFFFFFu;
-    // random.sample(NOBLES, P+1): partial Fisher-Yates over the 10 ids held as nibbles of a 64-bit word
     uint64_t ids = 0x9876543210ull;
     const uint4 r0 = philox(seed, game, 0, STREAM_NOBLES), r1 = philox(seed, game, 1, STREAM_NOBLES);
     const uint32_t rr[5] = {r0.x, r0.y, r0.z, r0.w, r1.x};
@@ -436,7 +433,17 @@ __device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t gam
         ids = (ids & ~(15ull << (4 * i)) & ~(15ull << (4 * j))) | (vj << (4 * i)) | (vi << (4 * j));
         list = (list & ~(15u << (4 * i))) | ((uint32_t)vj << (4 * i));
     }
-    e.meta = list | ((uint32_t)(P - 2) << 22);
+    return list;
+}
+
+// SplendorState.__init__ (splendor_model.py:53-93) with Philox nobles and lazily drawn decks
+template <int P>
+__device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t game, const uint32_t *rk = nullptr)
+{
+    const uint32_t n = P == 2 ? 4 : (P == 3 ? 5 : 7);
+    e.bank = n * (ONES6 & ~(1u << YSH)) | (5u << YSH);
+    e.k[0] = 0xFFFFFFFFu; e.k[1] = 0x3FFFFFFFu; e.k[2] = 0x0FFFFFFFu;
+    e.meta = sample_nobles<P>(seed, game) | ((uint32_t)(P - 2) << 22);
     DeckSrc src{nullptr, seed, game, rk};
     e.d[0] = e.d[1] = e.d[2] = 0;
 #pragma unroll 1
@@ -447,6 +454,53 @@ __device__ __forceinline__ void reset_env(Env<P> &e, uint64_t seed, uint64_t gam
     }
 #pragma unroll
     for (int p = 0; p < P; p++) { e.pg[p] = 0; e.pc[p] = 0; e.pr[p] = 0x00FFFFFFu; e.pi[p] = 0; }
+}
+
+// The same initial state with the WHOLE deck order drawn up front into `lists` (90 bytes, the explicit-list format of
+// spl_inject: a tier's next card is the last entry of its list).  The d-th card of a tier is the same card deal()
+// would draw lazily - the order is a function of (seed, game) only - so a game played from here is identical, but its
+// in-game deals are one byte load instead of a Philox call and a bit select.  The playout kernel keeps the lists in
+// shared memory; the draws run here with all 32 lanes of the warp active instead of ~7 lanes inside the step loop.
+// On return the env is in explicit-list form (deck counts in k[0]); lists_to_masks() converts it back.
+template <int P>
+__device__ __forceinline__ void reset_env_lists(Env<P> &e, uint64_t seed, uint64_t game, const uint32_t *rk, uint8_t *lists)
+{
+    const uint32_t n = P == 2 ? 4 : (P == 3 ? 5 : 7);
+    e.bank = n * (ONES6 & ~(1u << YSH)) | (5u << YSH);
+    e.k[0] = 0xFFFFFFFFu; e.k[1] = 0x3FFFFFFFu; e.k[2] = 0x0FFFFFFFu;
+    e.meta = sample_nobles<P>(seed, game) | ((uint32_t)(P - 2) << 22);
+    const DeckSrc philox_src{nullptr, seed, game, rk};
+#pragma unroll 1
+    for (int t = 0; t < 3; t++) {
+        const int size = t == 0 ? 40 : (t == 1 ? 30 : 20), base = t == 0 ? 0 : (t == 1 ? 40 : 70);
+#pragma unroll 1
+        for (int d = 0; d < size; d++) lists[base + size - 1 - d] = (uint8_t)deal(e, t, philox_src);
+    }
+    e.k[0] = 40u | 30u << 8 | 20u << 16; e.k[1] = 0; e.k[2] = 0;
+    const DeckSrc list_src{lists, seed, game, rk};
+    e.d[0] = e.d[1] = e.d[2] = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) e.d[i >> 2] |= deal<P, true>(e, i >> 2, list_src) << (8 * (i & 3));
+#pragma unroll
+    for (int p = 0; p < P; p++) { e.pg[p] = 0; e.pc[p] = 0; e.pr[p] = 0x00FFFFFFu; e.pi[p] = 0; }
+}
+// explicit-list deck counts (k[0] bytes) + lists -> the counter-based form: one bit per card still in its deck
+template <int P>
+__device__ __forceinline__ void lists_to_masks(Env<P> &e, const uint8_t *lists)
+{
+    const uint32_t counts = e.k[0];
+    uint32_t k0 = 0, k1 = 0, k2 = 0;
+    for (int t = 0; t < 3; t++) {
+        const int base = t == 0 ? 0 : (t == 1 ? 40 : 70), cnt = (int)byte_of(counts, t);
+        for (int i = 0; i < cnt; i++) {
+            const int pos = (int)lists[base + i] - base;
+            if (t == 0 && pos < 32) k0 |= 1u << pos;
+            else if (t == 0) k2 |= 1u << (20 + pos - 32);
+            else if (t == 1) k1 |= 1u << pos;
+            else k2 |= 1u << pos;
+        }
+    }
+    e.k[0] = k0; e.k[1] = k1; e.k[2] = k2;
 }
 
 // ------------------------------------------------------------------------------------------------ legal actions
@@ -830,7 +884,7 @@ __device__ __forceinline__ bool decode_and_check(const Env<P> &e, const Tables &
 
 // ------------------------------------------------------------------------------------------------ successor
 // generateSuccessor + GameRule.update.  Returns the acting agent's score delta.
-template <int P>
+template <int P, bool LISTS = false>
 __device__ __forceinline__ int apply_action(Env<P> &e, const Choice &ch, const DeckSrc &src)
 {
     const int seat = seat_of(e.meta);
@@ -851,7 +905,7 @@ __device__ __forceinline__ int apply_action(Env<P> &e, const Choice &ch, const D
         if (tier == 1) w = e.d[1];
         if (tier == 2) w = e.d[2];
         const uint32_t id = byte_of(w, col);
-        w = set_byte(w, col, deal(e, tier, src));
+        w = set_byte(w, col, deal<P, LISTS>(e, tier, src));
         if (tier == 0) e.d[0] = w; else if (tier == 1) e.d[1] = w; else e.d[2] = w;
         if (ch.type == T_RESERVE) rv = set_byte(rv, __popc(~rv & 0x00808080u), id);
     } else if (ch.type == T_BUY_RESERVE) {

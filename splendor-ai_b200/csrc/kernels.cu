@@ -132,17 +132,24 @@ __global__ void __launch_bounds__(BLOCK, SPL_PLAYOUT_MINBLOCKS) playout_kernel(c
 {
     __shared__ Tables sT;
     __shared__ unsigned long long sctr[16];
+    // FRESH: every game's whole deck order, drawn at reset (reset_env_lists); 92-byte pitch = 23 words, odd, so the 32
+    // lanes of a warp writing the same entry hit 32 different banks
+    constexpr int LIST_PITCH = 92;
+    __shared__ __align__(4) uint8_t s_lists[FRESH ? BLOCK * LIST_PITCH : 4];
     if (threadIdx.x < 16) sctr[threadIdx.x] = 0;
     stage_tables(sT);
 
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = g < a.n_games;
+    uint8_t *const my_lists = s_lists + (FRESH ? threadIdx.x * LIST_PITCH : 0);
     Env<P> e;
     int t = 0, kind = SPL_END_NONE;
     if (live) {
         DeckSrc src{nullptr, a.seed, (!FRESH && a.game_ids) ? a.game_ids[g] : a.first_game + (uint64_t)g, a.rk};
-        if (FRESH) reset_env(e, a.seed, src.game, a.rk);
-        else {
+        if (FRESH) {
+            reset_env_lists(e, a.seed, src.game, a.rk, my_lists);
+            src.lists = my_lists;
+        } else {
             load_env(e, a.state, a.n_games, g);
             src.lists = a.decks ? a.decks + g * SPL_DECK_BYTES : nullptr;
         }
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(BLOCK, SPL_PLAYOUT_MINBLOCKS) playout_kernel(c
             const int total = count_legal(e, sT, c, f);
             select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
             if (__builtin_expect(t < a.trace_len, 0)) a.trace[(int64_t)t * a.n_games + g] = (int16_t)ch.idx;  // trace_len is 0 without a trace
-            apply_action(e, ch, src);
+            apply_action<P, FRESH>(e, ch, src);
             t++;
         }
     }
@@ -184,7 +191,10 @@ __global__ void __launch_bounds__(BLOCK, SPL_PLAYOUT_MINBLOCKS) playout_kernel(c
         atomicAdd(&sctr[SPL_CTR_NOBLES], nob);
         if (a.steps) a.steps[g] = (int16_t)t;
         if (a.end_kind) a.end_kind[g] = (uint8_t)kind;
-        if (a.state) store_env(e, a.state, a.n_games, g);
+        if (a.state) {
+            if (FRESH) lists_to_masks(e, my_lists);  // back to the counter-based deck form of the ABI
+            store_env(e, a.state, a.n_games, g);
+        }
     }
     __syncthreads();
     if (a.counters && threadIdx.x < 16 && sctr[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], sctr[threadIdx.x]);

@@ -164,7 +164,10 @@ template <int P> static int t_playout(uint32_t *w, bool fresh, const uint8_t *li
 {
     Env<P> e;
     DeckSrc src{lists, seed, game};
-    if (fresh) reset_env(e, seed, game); else ld(e, w);
+    uint8_t drawn[92];  // fresh games: the kernel's form - the whole deck order drawn at reset, in-game deals pop the lists
+    uint32_t rk[20];
+    philox_round_keys(seed, rk);
+    if (fresh) { reset_env_lists(e, seed, game, rk, drawn); src.lists = drawn; src.rk = rk; } else ld(e, w);
     int t = 0;
     for (int p = 0; p < P; p++) t += e.pi[p] & 0xFFFFu;
     const int t_end = t + max_steps;
@@ -176,16 +179,17 @@ template <int P> static int t_playout(uint32_t *w, bool fresh, const uint8_t *li
         Ctx c; FamilyCounts f; Choice ch;
         make_ctx(e, T, c);
         const int total = count_legal(e, T, c, f);
-        const uint32_t r = philox(seed, game, (uint32_t)t, STREAM_ACTION).x;
+        const uint32_t r = philox_rk(rk, game, (uint32_t)t, STREAM_ACTION).x;
         select_legal(e, T, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
         if (trace && t < trace_len) trace[t] = (int16_t)ch.idx;
-        apply_action(e, ch, src);
+        if (fresh) apply_action<P, true>(e, ch, src); else apply_action(e, ch, src);
         t++;
     }
     int oc[P], sc[P];
     final_scores(e, sc, oc);
     for (int p = 0; p < P; p++) score2[p] = sc[p];
     *kind_out = kind;
+    if (fresh) lists_to_masks(e, drawn);
     st(e, w);
     return t;
 }
