@@ -205,6 +205,41 @@ def other_kernels(pkg, dev, N=262_144, P=2, reps=10):
                             "frac": N * b / (ms * 1e-3) / 1e9 / peak} for k, (ms, b) in runs.items()}}
 
 
+def other_sizes(pkg, dev, reps=5):
+    """The fused playout at the sizes of BASELINE configs 3 and 5 (a 2^20-game launch each; config 5's 2^24 sweep is 16 of
+    them per GPU): CUDA-event timed launches, env-steps/s and the fraction of the HBM roofline at the algorithmic bytes per
+    env-step of the player count.  Informational: the headline stays config[1]."""
+    import torch
+
+    peak = 6533.8
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        peak = float(json.load(open(path))["hbm_gbs"])
+    lib = pkg._native.lib()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    out = {}
+    for P in (2, 4):
+        G = 1 << 20
+        ctr = torch.zeros(16, dtype=torch.int64, device=dev)
+        scratch = torch.zeros(16, dtype=torch.int64, device=dev)
+        for w in range(2):
+            pkg._native.check(lib.spl_playout(SEED, (1 << 40) + w * G, G, P, 0, MAX_STEPS, None, None, None, scratch.data_ptr(), None, 0, None, stream), "spl_playout")
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(reps):
+            pkg._native.check(lib.spl_playout(SEED, (1 << 40) + (2 + r) * G, G, P, 0, MAX_STEPS, None, None, None, ctr.data_ptr(), None, 0, None, stream), "spl_playout")
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        steps = int(ctr[1].item())
+        b = 2 * (8 + 4 * P) * 4 + 32  # state read + write + the per-step outputs, as BYTES_PER_STEP for 2 players
+        v = steps / (ms * reps * 1e-3)
+        out[f"{P}p_2^20_games_per_launch"] = {"ms_per_launch": ms, "env_steps_per_s": v, "algorithmic_bytes_per_env_step": b,
+                                              "GBps": v * b / 1e9, "frac": v * b / 1e9 / peak}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import numpy as np
@@ -289,12 +324,16 @@ def run_b200(args):
     D.allreduce_counters(e2e_steps)
     e2e_value = int(e2e_steps.item()) / e2e_s
 
-    other = None
+    other = sizes = None
     if rank == 0:
         try:
             other = other_kernels(pkg, dev)
         except Exception as exc:  # informational section: never fail the headline measurement because of it
             other = {"error": repr(exc)}
+        try:
+            sizes = other_sizes(pkg, dev)
+        except Exception as exc:
+            sizes = {"error": repr(exc)}
     D.barrier()
     D.shutdown()
     if rank != 0:
@@ -326,6 +365,7 @@ def run_b200(args):
                      "note": "state lives in registers for the whole game; the limiter is instruction issue, not DRAM (DESIGN.md)"},
         "clocks": clock_info,
         "other_kernels": other,
+        "other_sizes": sizes,
     }
     if world == 1 and not args.no_cpu_baseline:
         v, cores, games, steps, dt = cpu_port_throughput(P, args.cpu_seconds)

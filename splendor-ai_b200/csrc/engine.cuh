@@ -72,7 +72,7 @@ struct Tables {
     // return-multiset generating functions (see ReturnPoly below): (1 + x + .. + x^lvl)^n and 1 / (1 + x + .. + x^lvl)
     // as base-256 digit strings modulo 2^32
     uint32_t poly_pow[3][8];    // [lvl-1][n], n = 0..6
-    uint32_t poly_inv[4];       // [lvl]
+    uint32_t poly_inv[16];      // [gems held of the colour] (level = min(held, 3))
     uint32_t recip[68];         // ceil(2^31 / d), d = 1..64 (small_div)
     uint2 buyrow[256];          // card[] for count_legal's affordability test: guard bits already set in the cost (.x | H6),
                                 // and indexed by the raw slot byte (0xFF = empty slot -> filler), so no masking of the id
@@ -223,10 +223,11 @@ __host__ __device__ constexpr Tables make_tables()
         uint32_t p = 1;
         for (int n = 0; n < 8; n++) { T.poly_pow[l - 1][n] = p; p *= unit[l]; }
     }
-    for (int l = 0; l < 4; l++) {  // Newton iteration for the inverse of an odd number modulo 2^32
-        uint32_t x = unit[l];
-        for (int it = 0; it < 5; it++) x *= 2u - unit[l] * x;
-        T.poly_inv[l] = x;
+    for (int h = 0; h < 16; h++) {  // Newton iteration for the inverse of an odd number modulo 2^32
+        const uint32_t u = unit[h < 3 ? h : 3];
+        uint32_t x = u;
+        for (int it = 0; it < 5; it++) x *= 2u - u * x;
+        T.poly_inv[h] = x;
     }
     for (int i = 0; i < 256; i++) T.buyrow[i] = uint2{T.card[i & 127].x | H6, T.card[i & 127].y & 31u};  // .y: the colour's bit offset only
     for (int d = 1; d <= 64; d++) T.recip[d] = (uint32_t)(((1ull << 31) + (uint64_t)d - 1) / (uint64_t)d);
@@ -519,6 +520,7 @@ struct Ctx {
     uint32_t S, near;      // S: nobles already earned (bit = list position); near: bit 5*colour_field_shift+k
     uint32_t h1, h2, h3;   // field masks: gems held >= 1 / 2 / 3
     uint32_t A1, A4;       // field masks (normal colours): bank >= 1 / >= 4
+    uint32_t A1g, A4g;     // the same as guard bits (bit 5f+4), which is how the SWAR compare produces them
     uint32_t occ;          // 12-bit mask of non-empty board slots
     int nS, hold, yellow, n_resv, nA, Lmin, Lmax;
     bool bank_yellow;
@@ -545,11 +547,12 @@ __device__ __forceinline__ void make_ctx(const Env<P> &e, const Tables &T, Ctx &
     c.hold = (int)hsum6(c.gems);
     c.yellow = (int)field(c.gems, YSH);
     c.h1 = ge_mask(c.gems, 1); c.h2 = ge_mask(c.gems, 2); c.h3 = ge_mask(c.gems, 3);
-    c.A1 = ge_mask(c.bank, 1) & NORMAL_FIELDS; c.A4 = ge_mask(c.bank, 4) & NORMAL_FIELDS;
+    c.A1g = (c.bank + 15u * ONES6) & (H6 & ~(16u << YSH)); c.A4g = (c.bank + 12u * ONES6) & (H6 & ~(16u << YSH));
+    c.A1 = compress6(c.A1g); c.A4 = compress6(c.A4g);  // dead code in kernels that only count and select
     c.bank_yellow = field(c.bank, YSH) > 0;
     c.n_resv = __popc(~c.resv & 0x00808080u);
     c.occ = occupied4(e.d[0]) | occupied4(e.d[1]) << 4 | occupied4(e.d[2]) << 8;
-    c.nA = __popc(c.A1);
+    c.nA = __popc(c.A1g);
     c.Lmax = min(c.nA, 3);
     c.Lmin = c.hold <= 7 ? c.Lmax : (c.hold == 8 ? min(c.nA, 2) : min(c.nA, 1));
 }
@@ -622,9 +625,9 @@ __device__ __forceinline__ void collect_groups(const Tables &T, const Ctx &c, Fa
 #pragma unroll
     for (int n = 0; n < 5; n++) {
         const int fl = field_of_normal(n);
-        const uint32_t inv = T.poly_inv[min(field(c.gems, 5 * fl), 3u)];
-        Js[n] = (c.A4 >> fl & 1u) ? inv : 0u;
-        Jd[n] = (c.A1 >> fl & 1u) ? inv : 0u;
+        const uint32_t inv = T.poly_inv[field(c.gems, 5 * fl) & 15u];
+        Js[n] = (c.A4g >> (5 * fl + 4) & 1u) ? inv : 0u;
+        Jd[n] = (c.A1g >> (5 * fl + 4) & 1u) ? inv : 0u;
     }
     // digit selectors: a group taking L gems returns e_L = max(hold + L - 10, 0) <= 3; collect_same returns e_2
     const uint32_t e1 = (uint32_t)max(c.hold - 9, 0), e2 = (uint32_t)max(c.hold - 8, 0), e3 = (uint32_t)max(c.hold - 7, 0);
