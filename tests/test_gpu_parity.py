@@ -290,6 +290,61 @@ def test_host_buffer_abi_call(pkg, oracle):
     assert np.array_equal(score2, sc) and np.array_equal(steps.astype(np.int32), st) and np.array_equal(ctr, c)
 
 
+def test_host_buffer_abi_call_in_chunks(pkg, oracle):
+    """The chunked form of spl_playout_host (>= 16,384 games: copies and kernels of several chunks overlap on internal
+    streams), with a batch size that leaves a ragged last chunk and a ragged last block."""
+    import ctypes as C
+
+    N, P, seed, first = 20_011, 2, 77, 5_000
+    eng = pkg.BatchedSplendor(N, P, seed=seed, first_game=first)
+    lists_d, nobles_d = eng.reset(want_lists=True)
+    lists, nobles = lists_d.cpu().numpy(), nobles_d.cpu().numpy()
+    score2, steps, kind = np.zeros((N, P), np.int8), np.zeros(N, np.int16), np.zeros(N, np.uint8)
+    ctr = np.zeros(16, np.int64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = pkg._native.lib().spl_playout_host(p(lists), p(nobles), seed, first, N, P, 0, 1000, p(score2), p(steps), p(kind), p(ctr), None)
+    assert rc == 0, pkg._native.lib().spl_error_string(rc)
+    sc, st, c = oracle.playout_many(seed, first, N, P, False, 1000, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(score2, sc) and np.array_equal(steps.astype(np.int32), st) and np.array_equal(ctr, c)
+
+
+@pytest.mark.parametrize("knob", [{"SPL_PLAYOUT_BLOCK": "32"}, {"SPL_PLAYOUT_BLOCK": "96"}, {"SPL_HOST_CHUNKS": "3"}])
+def test_tuning_knobs_do_not_change_results(pkg, knob):
+    """SPL_PLAYOUT_BLOCK (threads per block of the playout kernel; also the pitch of the shared-memory deck lists) and
+    SPL_HOST_CHUNKS are read once per process, so the other setting runs in a child process; every per-game output and
+    the final states must be identical."""
+    import subprocess
+    import sys
+    import tempfile
+
+    code = (
+        "import sys, numpy as np, torch, ctypes as C\n"
+        "sys.path.insert(0, sys.argv[1])\n"
+        "import splendor_ai_b200 as pkg\n"
+        "out = pkg.playout_games(5000, 3, seed=5, first_game=123, trace_len=64, want_final_state=True)\n"
+        "N, P = 17000, 2\n"
+        "eng = pkg.BatchedSplendor(N, P, seed=6, first_game=9)\n"
+        "l, n = eng.reset(want_lists=True)\n"
+        "l, n = l.cpu().numpy(), n.cpu().numpy()\n"
+        "sc, st, kd, ctr = np.zeros((N, P), np.int8), np.zeros(N, np.int16), np.zeros(N, np.uint8), np.zeros(16, np.int64)\n"
+        "p = lambda a: a.ctypes.data_as(C.c_void_p)\n"
+        "assert pkg._native.lib().spl_playout_host(p(l), p(n), 6, 9, N, P, 0, 1000, p(sc), p(st), p(kd), p(ctr), None) == 0\n"
+        "np.savez(sys.argv[2], host_score=sc, host_steps=st, host_kind=kd, host_ctr=ctr, "
+        "**{k: out[k].cpu().numpy() for k in ('score2', 'steps', 'end_kind', 'counters', 'trace', 'final_state')})\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    results = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for i, extra in enumerate(({}, knob)):
+            env = {k: v for k, v in os.environ.items() if k not in ("SPL_PLAYOUT_BLOCK", "SPL_HOST_CHUNKS")}
+            env.update(extra)
+            path = os.path.join(tmp, f"r{i}.npz")
+            subprocess.run([sys.executable, "-c", code, root, path], check=True, env=env, timeout=600)
+            results.append(dict(np.load(path)))
+    for key in results[0]:
+        assert np.array_equal(results[0][key], results[1][key]), (knob, key)
+
+
 @pytest.mark.parametrize("P", [2, 3, 4])
 def test_fuzzed_states_on_gpu(pkg, oracle, P):
     """Arbitrary hand-built states (tests/fuzz_states.py: 10-gem holders, drained banks, empty slots/decks, 7-card cap,
