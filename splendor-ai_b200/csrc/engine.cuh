@@ -69,7 +69,7 @@ struct Tables {
     uint16_t cwr2_pair[2][16];  // [k==4][x]: k others held>=1 -> bits of the i<j entries of combinations_with_replacement(k,2)
     uint16_t cwr2_dbl[2][16];   // [k==4][y]: held>=2 -> bits of the (i,i) entries
     uint16_t cwr3[512];         // k=3: x | y<<3 | z<<6 (held >=1/>=2/>=3) -> bits of combinations_with_replacement(3,3)
-    // return-multiset generating functions (see ReturnPoly below): (1 + x + .. + x^lvl)^n and 1 / (1 + x + .. + x^lvl)
+    // return-multiset generating functions (see collect_groups below): (1 + x + .. + x^lvl)^n and 1 / (1 + x + .. + x^lvl)
     // as base-256 digit strings modulo 2^32
     uint32_t poly_pow[3][8];    // [lvl-1][n], n = 0..6
     uint32_t poly_inv[16];      // [gems held of the colour] (level = min(held, 3))
