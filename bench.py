@@ -362,7 +362,7 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak,
                      "traffic": traffic, "kernel": "playout_kernel<2,true>", "peak_source": peak_src,
                      "algorithmic_bytes_per_env_step": BYTES_PER_STEP,
-                     "note": "state lives in registers for the whole game; the limiter is instruction issue, not DRAM (DESIGN.md)"},
+                     "note": "state lives in registers for the whole game; the limiter is the integer ALU pipe and, at this batch size, the dependent chain of the longest games - not DRAM (DESIGN.md section 6)"},
         "clocks": clock_info,
         "other_kernels": other,
         "other_sizes": sizes,
