@@ -195,6 +195,17 @@ int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t 
                      int P, uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind,
                      int64_t *counters, void *stream);
 
+/* The same without the final synchronise, for callers that pipeline batches (a rollout loop that prepares batch k+1
+ * while batch k plays): returns as soon as the copies and kernels are queued.  The output arrays and `counters`
+ * (16 x int64, OVERWRITTEN, not accumulated) are valid once `stream` has reached the end of the queued work
+ * (cudaStreamSynchronize / an event recorded after the call); all host buffers must stay alive until then and should be
+ * pinned, or the copies degrade to synchronous ones.  `slot` (0 or 1) picks one of two independent staging areas: calls
+ * in flight at the same time must use different slots and different streams; a slot is reused only after its previous
+ * call has completed (the library orders that on the device if the caller does not). */
+int spl_playout_host_async(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t seed, uint64_t first_game, int64_t N,
+                           int P, uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind,
+                           int64_t *counters, int slot, void *stream);
+
 /* Device the library should use for its staging buffers and table upload (default: current device). */
 int spl_warmup(void);
 

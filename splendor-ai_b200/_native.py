@@ -25,7 +25,7 @@ CTR_NAMES = ("games", "steps", "wins0", "wins1", "wins2", "wins3", "ties0", "tie
 
 EXPORTS = ("spl_abi_version", "spl_state_words", "spl_last_cuda_error", "spl_error_string", "spl_warmup", "spl_reset",
            "spl_inject", "spl_legal_mask", "spl_step", "spl_final_scores", "spl_observe", "spl_playout", "spl_playout_from",
-           "spl_env_step", "spl_playout_host", "spl_undo", "spl_count_legal", "spl_expand", "spl_masked_sample",
+           "spl_env_step", "spl_playout_host", "spl_playout_host_async", "spl_undo", "spl_count_legal", "spl_expand", "spl_masked_sample",
            "spl_minimax_eval", "spl_minimax2")
 
 
@@ -89,6 +89,7 @@ def lib():
         L.spl_playout_from.argtypes = [vp, vp, u64, u64, vp, i64, i32, u32, i32, vp, vp, vp, vp, vp, i32, vp]
         L.spl_env_step.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, u32, vp]
         L.spl_playout_host.argtypes = [vp, vp, u64, u64, i64, i32, u32, i32, vp, vp, vp, vp, vp]
+        L.spl_playout_host_async.argtypes = [vp, vp, u64, u64, i64, i32, u32, i32, vp, vp, vp, vp, i32, vp]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = the .so does not match include/splendor_b200.h
         _lib = L

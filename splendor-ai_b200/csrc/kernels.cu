@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -1014,31 +1015,40 @@ struct Staging {
     }
 };
 std::mutex g_stage_mu;
-Staging g_stage;
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-}  // namespace
 
-int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t seed, uint64_t first_game, int64_t N, int P,
-                     uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind, int64_t *counters,
-                     void *stream_)
-{
-    if (!deck_lists || !nobles || N < 0 || P < 2 || P > 4) return SPL_E_BADARG;
-    if (int rc = check_device()) return rc;
-    if (N == 0) return SPL_OK;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    std::lock_guard<std::mutex> lock(g_stage_mu);
-    // The batch is cut into chunks that travel on separate internal streams: the H2D copy of chunk k+1 and the D2H copy
-    // of chunk k-1 overlap the kernels of chunk k (and the chunk kernels, latency-bound at this size, overlap each other).
-    constexpr int MAX_CHUNKS = 8, HOST_CHUNKS_DEFAULT = 4;
-    static cudaStream_t side[MAX_CHUNKS] = {};
-    static cudaEvent_t ev_start = nullptr, ev_done[MAX_CHUNKS] = {};
-    if (!ev_start) {
+// One of the two independent pipelines of the host-buffer path: its own staging memory, chunk streams and events, so
+// that two calls in flight (spl_playout_host_async on alternating slots) share nothing but the GPU.
+constexpr int HOST_SLOTS = 2, MAX_CHUNKS = 8, HOST_CHUNKS_DEFAULT = 4;
+struct HostSlot {
+    Staging stage;
+    cudaStream_t side[MAX_CHUNKS] = {};
+    cudaEvent_t ev_start = nullptr, ev_done[MAX_CHUNKS] = {}, ev_call_done = nullptr;
+    bool used = false;
+    int init()
+    {
+        if (ev_start) return SPL_OK;
         CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_call_done, cudaEventDisableTiming));
         for (int c = 0; c < MAX_CHUNKS; c++) {
             CK(cudaStreamCreateWithFlags(&side[c], cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
         }
+        return SPL_OK;
     }
+};
+HostSlot g_slots[HOST_SLOTS];
+
+// Everything of a host-buffer playout up to (not including) the wait for its completion: on return the copies and
+// kernels are queued, `ctr_out` (host, 16 x int64) and the output arrays are written when `stream` reaches the end of
+// the queued work.  Caller holds g_stage_mu.
+int playout_host_enqueue(HostSlot &S, const uint8_t *deck_lists, const uint8_t *nobles, uint64_t seed, uint64_t first_game, int64_t N,
+                         int P, uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind, int64_t *ctr_out,
+                         cudaStream_t stream)
+{
+    if (int rc = S.init()) return rc;
+    // The batch is cut into chunks that travel on separate internal streams: the H2D copy of chunk k+1 and the D2H copy
+    // of chunk k-1 overlap the kernels of chunk k (and the chunk kernels, latency-bound at this size, overlap each other).
     static int want_chunks = 0;
     if (!want_chunks) {  // SPL_HOST_CHUNKS: 1..8, a tuning knob (profiles/r1q_playout.md)
         const char *s = getenv("SPL_HOST_CHUNKS");
@@ -1054,16 +1064,20 @@ int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t 
                  o_nobles = o_decks + align256((size_t)N * SPL_DECK_BYTES), o_score = o_nobles + align256((size_t)N * 5),
                  o_steps = o_score + align256((size_t)N * P), o_kind = o_steps + align256((size_t)N * 2),
                  o_ctr = o_kind + align256((size_t)N), total = o_ctr + 256;
-    if (int rc = g_stage.ensure(total)) return rc;
-    char *b = (char *)g_stage.p;
+    if (total > S.stage.cap && S.used) CK(cudaEventSynchronize(S.ev_call_done));  // growing frees the old buffer: let its last user finish
+    if (int rc = S.stage.ensure(total)) return rc;
+    char *b = (char *)S.stage.p;
+    // a slot is reused only after the previous call on it has completed (device-side wait: a caller that alternates
+    // slots as documented never blocks here; one that does not is serialised instead of corrupted)
+    if (S.used) CK(cudaStreamWaitEvent(stream, S.ev_call_done, 0));
     CK(cudaMemsetAsync(b + o_ctr, 0, 128, stream));
-    CK(cudaEventRecord(ev_start, stream));
+    CK(cudaEventRecord(S.ev_start, stream));
     size_t state_off = o_state;
     for (int c = 0; c < n_chunks; c++) {
         const int64_t lo = (int64_t)c * per, n = (lo + per <= N ? per : N - lo);
         if (n <= 0) break;
-        cudaStream_t s = side[c];
-        CK(cudaStreamWaitEvent(s, ev_start, 0));
+        cudaStream_t s = S.side[c];
+        CK(cudaStreamWaitEvent(s, S.ev_start, 0));
         char *st = b + state_off;  // each chunk is its own chunk-major state batch of n envs
         state_off += align256((size_t)n * W);
         CK(cudaMemcpyAsync(b + o_decks + lo * SPL_DECK_BYTES, deck_lists + lo * SPL_DECK_BYTES, (size_t)n * SPL_DECK_BYTES, cudaMemcpyHostToDevice, s));
@@ -1076,15 +1090,48 @@ int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t 
         if (score2) CK(cudaMemcpyAsync(score2 + lo * P, b + o_score + lo * P, (size_t)n * P, cudaMemcpyDeviceToHost, s));
         if (steps) CK(cudaMemcpyAsync(steps + lo, b + o_steps + lo * 2, (size_t)n * 2, cudaMemcpyDeviceToHost, s));
         if (end_kind) CK(cudaMemcpyAsync(end_kind + lo, b + o_kind + lo, (size_t)n, cudaMemcpyDeviceToHost, s));
-        CK(cudaEventRecord(ev_done[c], s));
-        CK(cudaStreamWaitEvent(stream, ev_done[c], 0));
+        CK(cudaEventRecord(S.ev_done[c], s));
+        CK(cudaStreamWaitEvent(stream, S.ev_done[c], 0));
     }
+    if (ctr_out) CK(cudaMemcpyAsync(ctr_out, b + o_ctr, 128, cudaMemcpyDeviceToHost, stream));
+    CK(cudaEventRecord(S.ev_call_done, stream));
+    S.used = true;
+    return SPL_OK;
+}
+}  // namespace
+
+int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t seed, uint64_t first_game, int64_t N, int P,
+                     uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind, int64_t *counters,
+                     void *stream_)
+{
+    if (!deck_lists || !nobles || N < 0 || P < 2 || P > 4) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) return SPL_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    std::lock_guard<std::mutex> lock(g_stage_mu);
     int64_t ctr[16];
-    CK(cudaMemcpyAsync(ctr, b + o_ctr, 128, cudaMemcpyDeviceToHost, stream));
+    if (int rc = playout_host_enqueue(g_slots[0], deck_lists, nobles, seed, first_game, N, P, flags, max_steps, score2, steps, end_kind,
+                                      ctr, stream))
+        return rc;
     CK(cudaStreamSynchronize(stream));
     if (counters)
         for (int i = 0; i < 16; i++) counters[i] += ctr[i];
     return SPL_OK;
+}
+
+int spl_playout_host_async(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t seed, uint64_t first_game, int64_t N, int P,
+                           uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind, int64_t *counters,
+                           int slot, void *stream_)
+{
+    if (!deck_lists || !nobles || N < 0 || P < 2 || P > 4 || slot < 0 || slot >= HOST_SLOTS) return SPL_E_BADARG;
+    if (int rc = check_device()) return rc;
+    if (N == 0) {
+        if (counters) memset(counters, 0, 128);
+        return SPL_OK;
+    }
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    return playout_host_enqueue(g_slots[slot], deck_lists, nobles, seed, first_game, N, P, flags, max_steps, score2, steps, end_kind,
+                                counters, (cudaStream_t)stream_);
 }
 
 }  // extern "C"

@@ -308,6 +308,38 @@ def test_host_buffer_abi_call_in_chunks(pkg, oracle):
     assert np.array_equal(score2, sc) and np.array_equal(steps.astype(np.int32), st) and np.array_equal(ctr, c)
 
 
+def test_async_host_buffer_calls_pipeline_on_two_slots(pkg, oracle):
+    """spl_playout_host_async: six batches in flight pairwise on two slots / two streams with pinned buffers; every
+    batch's outputs and counters equal the oracle's (and so the synchronous call's)."""
+    N, P, seed = 18_000, 2, 31
+    lib = pkg._native.lib()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    batches = []
+    for b in range(6):
+        eng = pkg.BatchedSplendor(N, P, seed=seed, first_game=b * N)
+        lists_d, nobles_d = eng.reset(want_lists=True)
+        batches.append((lists_d.cpu().pin_memory(), nobles_d.cpu().pin_memory()))
+    torch.cuda.synchronize()
+    outs = [(torch.zeros((N, P), dtype=torch.int8).pin_memory(), torch.zeros(N, dtype=torch.int16).pin_memory(),
+             torch.zeros(N, dtype=torch.uint8).pin_memory(), torch.zeros(16, dtype=torch.int64).pin_memory()) for _ in range(6)]
+    for b in range(6):
+        slot = b & 1
+        lists, nobles = batches[b]
+        sc, st, kd, ctr = outs[b]
+        rc = lib.spl_playout_host_async(lists.data_ptr(), nobles.data_ptr(), seed, b * N, N, P, 0, 1000, sc.data_ptr(), st.data_ptr(),
+                                        kd.data_ptr(), ctr.data_ptr(), slot, streams[slot].cuda_stream)
+        assert rc == 0, lib.spl_error_string(rc)
+    for s in streams:
+        s.synchronize()
+    for b in range(6):
+        sc, st, kd, ctr = outs[b]
+        osc, ost, octr = oracle.playout_many(seed, b * N, N, P, False, 1000, nthreads=os.cpu_count() or 1)
+        assert np.array_equal(sc.numpy(), osc) and np.array_equal(st.numpy().astype(np.int32), ost), b
+        assert np.array_equal(ctr.numpy(), octr), b
+    assert lib.spl_playout_host_async(batches[0][0].data_ptr(), batches[0][1].data_ptr(), seed, 0, N, P, 0, 1000, None, None, None, None,
+                                      2, None) == pkg._native.SPL_E_BADARG  # only slots 0 and 1 exist
+
+
 @pytest.mark.parametrize("knob", [{"SPL_PLAYOUT_BLOCK": "32"}, {"SPL_PLAYOUT_BLOCK": "96"}, {"SPL_HOST_CHUNKS": "3"}])
 def test_tuning_knobs_do_not_change_results(pkg, knob):
     """SPL_PLAYOUT_BLOCK (threads per block of the playout kernel; also the pitch of the shared-memory deck lists) and
