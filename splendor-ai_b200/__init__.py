@@ -15,6 +15,10 @@ def __getattr__(name):  # torch is imported lazily so that `build()` works in a 
 
         engine = importlib.import_module(__name__ + ".engine")
         return engine if name == "engine" else getattr(engine, name)
+    if name in ("SplendorEnv", "SplendorVecEnv"):
+        import importlib
+
+        return getattr(importlib.import_module(__name__ + ".env"), name)
     if name in ("actions", "game_rule", "env", "template", "dist", "minimax", "game", "rollout", "sampling"):
         import importlib
 

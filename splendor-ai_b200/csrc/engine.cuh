@@ -386,10 +386,12 @@ struct DeckSrc {
 // BoardState.deal (splendor_model.py:95-99).  Counter-based decks: the d-th card dealt from a tier is the
 // floor(u*c)-th smallest id still in the deck (c cards left, u = Philox word of (seed, game, d, tier)) - a lazy
 // Fisher-Yates draw whose order is a function of (seed, game) only, never of the actions played.
+// The deck form is a property of the ENV (META_EXPLICIT, set by spl_inject), not of the batch: after a partial spl_reset of
+// an injected batch the reset envs are counter-based while the others still pop their lists.
 template <int P, bool LISTS = false>  // LISTS: the caller guarantees src.lists (no counter-based code is generated)
 __device__ __forceinline__ uint32_t deal(Env<P> &e, int tier, const DeckSrc &src)
 {
-    if (LISTS || src.lists) {  // explicit lists: pop from the end
+    if (LISTS || (src.lists && (e.meta & META_EXPLICIT))) {  // explicit lists: pop from the end
         uint32_t cnt = byte_of(e.k[0], tier);
         if (cnt == 0) return NONE8;
         cnt--;

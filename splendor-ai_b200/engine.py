@@ -63,7 +63,10 @@ class BatchedSplendor:
         elif where is None:
             self.game_ids = None
         w = None if where is None else where.to(device=self.device, dtype=torch.uint8).contiguous()
-        self.decks = None
+        if where is None:
+            self.decks = None
+        # a partial reset of an injected batch keeps the deck lists: the kernels pick the deck form per env (an env that
+        # was reset draws from its counter-based deck, the others keep popping their explicit lists)
         lists = torch.empty((self.N, 90), dtype=torch.uint8, device=self.device) if want_lists else None
         nobles = torch.empty((self.N, 5), dtype=torch.uint8, device=self.device) if want_lists else None
         with torch.cuda.device(self.device):
@@ -71,8 +74,11 @@ class BatchedSplendor:
                                          _ptr(lists), _ptr(nobles), _stream(self.device)), "spl_reset")
         return (lists, nobles) if want_lists else None
 
-    def inject(self, deck_lists, nobles):
-        """Initial states from explicit deck orders ([N,90] card ids, reference list order) and noble ids ([N,>=P+1])."""
+    def inject(self, deck_lists, nobles, game_ids: torch.Tensor | None = None):
+        """Initial states from explicit deck orders ([N,90] card ids, reference list order) and noble ids ([N,>=P+1]).
+        game_ids (int64 [N]): the ids that key the in-kernel random choices (opponents, playouts) of these games."""
+        if game_ids is not None:
+            self.game_ids = game_ids.to(device=self.device, dtype=torch.int64).contiguous()
         d = torch.as_tensor(np.ascontiguousarray(deck_lists, dtype=np.uint8)).to(self.device)
         n = np.full((self.N, 5), 0xFF, np.uint8)
         nb = np.asarray(nobles, dtype=np.uint8)

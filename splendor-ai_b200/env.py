@@ -201,6 +201,17 @@ class SplendorVecEnv:
 
     def step(self, actions: torch.Tensor):
         a = actions.to(device=self.device, dtype=torch.int16)
+        if self.raise_on_illegal and self.legal_mask is not None:
+            # the reference raises before it mutates anything (splendor_env.py:139-153): test the action bits of the current
+            # masks first, so that a caught ValueError leaves every env, _done and legal_mask as they were
+            idx = a.to(torch.int64)
+            in_range = (idx >= 0) & (idx < NUM_ACTIONS)
+            word = torch.gather(self.legal_mask, 1, (idx.clamp(0, NUM_ACTIONS - 1) >> 5).unsqueeze(1)).squeeze(1)
+            legal = in_range & (((word >> (idx.clamp(0, NUM_ACTIONS - 1) & 31).to(torch.int32)) & 1) != 0)
+            bad_rows = torch.nonzero(~legal & ~self._done & (idx != -1))
+            if bad_rows.numel():
+                bad = int(bad_rows[0])
+                raise ValueError(f"the action {int(a[bad])} is illegal! (env {bad})")
         if bool(self._done.any()):  # next-step auto-reset: a fresh game id for every finished env
             self._episode += self._done.to(torch.int64)
             self._ids = self._game_ids()

@@ -1,0 +1,149 @@
+"""`-m gpu`: the recordings of the reference's own SplendorEnv (tests/golden/env_*.npz, oracle/gen_golden_env.py)
+replayed through the C ABI's spl_env_step, through SplendorVecEnv and through the drop-in SplendorEnv class - every
+observation (float32 bit pattern), reward, terminated flag, legal index set and state snapshot identical, call by call."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_env_episodes, scripted_choice
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import splendor_ai_b200 as p
+
+    p.build()
+    return p
+
+
+def unpack_mask(mask_row):
+    bits = np.unpackbits(np.ascontiguousarray(mask_row).view(np.uint8), bitorder="little")
+    return np.nonzero(bits)[0].astype(np.uint16)
+
+
+def snaps(eng, pkg):
+    return pkg.state.snapshots(eng.state_numpy(), eng.P)
+
+
+def nobles5(eps):
+    return np.stack([np.concatenate([e["nobles"], [255] * (5 - len(e["nobles"]))]) for e in eps]).astype(np.uint8)
+
+
+@pytest.mark.parametrize("name", ["env_2p", "env_3p", "env_4p"])
+def test_spl_env_step_replays_reference_env(pkg, name):
+    """spl_env_step with injected deck orders (explicit-list decks) and per-env game ids: learner move, in-kernel
+    Philox opponents, learner's mask + observation - against what the reference env returned."""
+    eps = load_env_episodes(name)
+    N, P, seed = len(eps), eps[0]["P"], eps[0]["seed"]
+    eng = pkg.BatchedSplendor(N, P, seed=seed, limit_rounds=True)
+    eng.inject(np.stack([e["decks"] for e in eps]), nobles5(eps), game_ids=torch.tensor([e["game"] for e in eps]))
+    learner = torch.tensor([e["my_id"] for e in eps], dtype=torch.int8)
+    for c in range(max(len(e["action"]) for e in eps)):
+        act = np.array([int(e["action"][c]) if c < len(e["action"]) else -1 for e in eps], np.int16)
+        obs, reward, term, illegal, mask = (x.cpu().numpy() for x in eng.env_step(learner, torch.from_numpy(act)))
+        sn = snaps(eng, pkg)
+        for i, e in enumerate(eps):
+            k = min(c, len(e["action"]) - 1)  # a finished episode stays where it ended (its action is -1 from then on)
+            where = (name, i, c)
+            assert illegal[i] == 0, where
+            if c < len(e["action"]):
+                assert reward[i] == e["reward"][c], where
+            assert bool(term[i]) == bool(e["terminated"][k]), where
+            assert np.array_equal(sn[i], e["snap"][k]), where
+            assert np.array_equal(unpack_mask(mask[i]), e["legal"][k]), where
+            assert np.array_equal(obs[i].view(np.uint32), e["obs"][k].view(np.uint32)), where
+
+
+@pytest.mark.parametrize("name", ["env_2p", "env_3p", "env_4p"])
+def test_vec_env_replays_reference_env(pkg, name):
+    """SplendorVecEnv (counter-based Philox decks, auto-reset) plays the recorded games from their (seed, game id) alone:
+    the recorded games ARE this repo's synthetic games, so nothing is injected."""
+    eps = load_env_episodes(name)
+    P, seed = eps[0]["P"], eps[0]["seed"]
+    for seat in range(P):
+        group = [e for e in eps if e["my_id"] == seat]
+        ids = [e["game"] for e in group]
+        assert ids == list(range(ids[0], ids[0] + len(ids)))
+        venv = pkg.SplendorVecEnv(len(group), P, seed=seed, first_game=ids[0], fixed_turn=seat)
+        obs, info = venv.reset()
+        assert info["my_id"].tolist() == [seat] * len(group)
+        obs, mask = obs.cpu().numpy(), info["legal_mask"].cpu().numpy()
+        for i, e in enumerate(group):
+            assert np.array_equal(obs[i].view(np.uint32), e["obs"][0].view(np.uint32)), (name, seat, i)
+            assert np.array_equal(unpack_mask(mask[i]), e["legal"][0]), (name, seat, i)
+        for c in range(1, max(len(e["action"]) for e in group)):
+            live = [c < len(e["action"]) for e in group]
+            # an env whose recorded episode is over has been auto-reset to a new game: play any legal action there
+            m = venv.get_legal_actions_mask(packed=True).cpu().numpy()
+            act = [int(e["action"][c]) if live[i] else int(unpack_mask(m[i])[0]) for i, e in enumerate(group)]
+            obs, reward, term, trunc, info = venv.step(torch.tensor(act, dtype=torch.int16))
+            obs, reward, term, mask = obs.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy(), info["legal_mask"].cpu().numpy()
+            assert not bool(trunc.any()) and not bool(info["illegal"].any())
+            for i, e in enumerate(group):
+                if not live[i]:
+                    continue
+                where = (name, seat, i, c)
+                assert reward[i] == e["reward"][c] and bool(term[i]) == bool(e["terminated"][c]), where
+                assert np.array_equal(obs[i].view(np.uint32), e["obs"][c].view(np.uint32)), where
+                assert np.array_equal(unpack_mask(mask[i]), e["legal"][c]), where
+
+
+def test_self_play_replay_of_scripted_episodes_reaches_the_round_cap(pkg):
+    """Every action of every seat of the scripted (hoarding) episodes, one per spl_env_step(SELF_PLAY) call: the state
+    after each learner-facing call, the terminated flag at every move and the 100-round cap (LimitRoundsGameRule)."""
+    for gi, e in enumerate(load_env_episodes("env_cap")):
+        P, me = e["P"], e["my_id"]
+        eng = pkg.BatchedSplendor(1, P, seed=e["seed"], limit_rounds=True)
+        eng.inject(e["decks"][None], nobles5([e]), game_ids=torch.tensor([e["game"]]))
+        call = 0
+
+        def at_call_boundary(obs, mask, term):
+            nonlocal call
+            sn = snaps(eng, pkg)[0]
+            seat = int(sn[27])
+            if seat != me and not term:
+                return
+            assert np.array_equal(sn, e["snap"][call]), (gi, call)
+            assert bool(term) == bool(e["terminated"][call]), (gi, call)
+            if seat == me:  # the rows are the next mover's
+                assert np.array_equal(unpack_mask(mask), e["legal"][call]), (gi, call)
+                assert np.array_equal(obs.view(np.uint32), e["obs"][call].view(np.uint32)), (gi, call)
+            call += 1
+
+        obs, _, term, _, mask = (x.cpu().numpy() for x in eng.env_step(None, torch.tensor([-1], dtype=torch.int16), self_play=True))
+        at_call_boundary(obs[0], mask[0], term[0])
+        for a in e["all_actions"]:
+            assert not term[0]
+            obs, _, term, illegal, mask = (x.cpu().numpy() for x in eng.env_step(None, torch.tensor([int(a)], dtype=torch.int16), self_play=True))
+            assert illegal[0] == 0
+            at_call_boundary(obs[0], mask[0], term[0])
+        assert term[0] and call == len(e["action"]), (gi, call)
+
+
+def test_dropin_env_class_replays_scripted_episodes(pkg, monkeypatch):
+    """The drop-in SplendorEnv class (host-side Agent opponents, GPU rule object) against the reference env: same
+    scripted opponents, same injected decks, same learner actions -> same observations, rewards, masks, terminations."""
+    from splendor_ai_b200 import game_rule as GR
+
+    class ScriptedAgent(pkg.template.Agent):
+        def SelectAction(self, actions, game_state, game_rule):
+            by_index = {GR.action_index(a, game_state, self.id): a for a in actions}
+            t = sum(len(ag.agent_trace.action_reward) for ag in game_state.agents)
+            return by_index[scripted_choice(sorted(by_index), t)]
+
+    for gi, e in enumerate(load_env_episodes("env_cap")):
+        P = e["P"]
+        monkeypatch.setattr(GR, "draw_initial_decks", lambda n, e=e: ([int(c) for c in e["decks"]], [int(x) for x in e["nobles"]]))
+        env = pkg.SplendorEnv([ScriptedAgent(0) for _ in range(P - 1)], shuffle_turns=False, fixed_turn=e["my_id"])
+        obs, info = env.reset()
+        assert info == {"my_id": e["my_id"]}
+        for c in range(len(e["action"])):
+            if c > 0:
+                obs, reward, terminated, truncated, _ = env.step(int(e["action"][c]))
+                assert reward == e["reward"][c] and bool(terminated) == bool(e["terminated"][c]) and truncated is False, (gi, c)
+            assert np.array_equal(np.asarray(obs, np.float32).view(np.uint32), e["obs"][c].view(np.uint32)), (gi, c)
+            assert np.array_equal(np.nonzero(env.get_legal_actions_mask())[0], e["legal"][c]), (gi, c)
+        with pytest.raises(ValueError):
+            env.step(3510)

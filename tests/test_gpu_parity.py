@@ -511,3 +511,35 @@ def test_self_play_env_step_matches_oracle(pkg, oracle, P):
                 assert reward[e] == oracle.step(orcs[e], int(act[e])), (e, it)
             assert kind[e] == oracle.game_ends(orcs[e], True), (e, it)
     assert (episode >= 1).mean() > 0.7  # one call = one move here, so a few long games are still running
+
+
+def test_partial_reset_of_an_injected_batch_keeps_both_deck_forms(pkg, oracle):
+    """inject() then reset(where=...): the reset envs draw from their counter-based Philox decks, the untouched ones keep
+    popping their explicit lists (the deck form is chosen per env from META_EXPLICIT, engine.cuh deal())."""
+    N, P, seed = 64, 2, 91
+    rng = np.random.default_rng(5)
+    lists = np.stack([np.concatenate([rng.permutation(40), 40 + rng.permutation(30), 70 + rng.permutation(20)]) for _ in range(N)]).astype(np.uint8)
+    nobles = np.stack([rng.permutation(10)[:P + 1] for _ in range(N)]).astype(np.uint8)
+    eng = pkg.BatchedSplendor(N, P, seed=seed)
+    eng.inject(lists, nobles)
+    orcs = [oracle.init(P, lists[e], nobles[e]) for e in range(N)]
+
+    def play(rounds):
+        for _ in range(rounds):
+            act = np.full(N, -1, np.int16)
+            for e in range(N):
+                if not oracle.game_ends(orcs[e], False):
+                    act[e] = rng.choice(oracle.legal(orcs[e]))
+                    oracle.step(orcs[e], int(act[e]))
+            _, _, illegal = eng.step(torch.from_numpy(act))
+            assert int(illegal.sum()) == 0
+            assert np.array_equal(snaps(eng, pkg), np.stack([o.snapshot() for o in orcs]))
+
+    play(25)
+    where = torch.from_numpy((np.arange(N) % 2 == 1).astype(np.uint8))
+    ids = torch.arange(1000, 1000 + N)
+    eng.reset(where=where, game_ids=ids)
+    for e in range(1, N, 2):
+        orcs[e] = oracle.init(P, *oracle.synth_game(seed, 1000 + e, P))
+    assert np.array_equal(snaps(eng, pkg), np.stack([o.snapshot() for o in orcs]))
+    play(60)  # reserve / buy moves of both kinds of env deal from their decks
