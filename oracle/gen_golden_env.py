@@ -120,7 +120,7 @@ def learner_choice(policy, rng, idxs, t):
     return int(rng.choice(idxs))
 
 
-def record_episode(P, seat, seed, game, policy, opponents, shuffle_turns, max_calls=400):
+def record_episode(P, seat, seed, game, policy, opponents, shuffle_turns, max_calls=400, pad=0):
     lists, nobles = O.synth_game(seed, game, P)
     log = []
     if opponents == "philox":
@@ -129,7 +129,7 @@ def record_episode(P, seat, seed, game, policy, opponents, shuffle_turns, max_ca
         agents = [ScriptedAgent(0, log) for _ in range(P - 1)]
     env = SplendorEnv(agents, shuffle_turns=shuffle_turns, fixed_turn=seat)
     rng = np.random.default_rng(seed * 1_000_003 + game)
-    ep = dict(P=P, my_id=seat, seed=seed, game=game, policy=policy, opponents=opponents, decks=np.asarray(lists, np.uint8),
+    ep = dict(P=P, my_id=seat, seed=seed, game=game, policy=policy, opponents=opponents, pad=pad, decks=np.asarray(lists, np.uint8),
               nobles=np.concatenate([nobles, [NONE] * (5 - len(nobles))]).astype(np.uint8),
               action=[], reward=[], terminated=[], obs=[], legal=[], snap=[], all_actions=log)
 
@@ -145,6 +145,15 @@ def record_episode(P, seat, seed, game, policy, opponents, shuffle_turns, max_ca
     with injected_decks(lists, nobles):
         obs, info = env.reset()
     assert info["my_id"] == seat
+    if pad:
+        # Harness edit of the reference's STATE (not its code): every agent's action trace gets `pad` placeholder entries
+        # right after reset, as if `pad` full rounds had been played without changing anything else.  Only the trace
+        # LENGTH is read by the rules (LimitRoundsGameRule.gameEnds, splendor/utils.py:19-23) and by observation feature 1
+        # (features.py:100-104).  With more than two players hoarding games end by score long before turn 100, so this is
+        # how the 100-round cap is reached for 3 and 4 players.
+        for ag in env.state.agents:
+            ag.agent_trace.action_reward.extend([({"type": "pass", "noble": None}, 0)] * pad)
+        obs = env._vectorize(env.state, env.my_turn)
     observe_call(obs, 0, env.game_rule.gameEnds(), -1)
     calls = 0
     while not ep["terminated"][-1] and calls < max_calls:
@@ -171,6 +180,7 @@ def pack(eps):
         legal_len=np.array([len(l) for e in eps for l in e["legal"]], np.int32),
         legal_flat=np.concatenate([l for e in eps for l in e["legal"]]),
         n_all=np.array([len(e["all_actions"]) for e in eps], np.int32), all_actions=cat("all_actions", np.int16),
+        pad=np.array([e["pad"] for e in eps], np.int32),
     )
 
 
@@ -190,19 +200,10 @@ if __name__ == "__main__":
             continue
         t0, eps, game = time.time(), [], first
         if P is None:
-            # scripted hoarders on every seat: keep the first game of each player count that runs into the 100-round cap
-            # (forced purchases end most hoarding games by score first), plus one that ends by score
-            def capped(e):
-                return all(e["snap"][-1][28 + 20 * i + 18] == 100 for i in range(e["P"]))
-            for PP, seat in ((2, 0), (2, 1), (3, 1), (4, 3)):
-                for attempt in range(40):
-                    e = record_episode(PP, seat, seed, game, "scripted", "scripted", False)
-                    game += 1
-                    if capped(e) or (PP, seat) == (2, 0):
-                        eps.append(e)
-                        break
-                else:
-                    raise SystemExit("no capped game found for %d players" % PP)
+            # scripted hoarders on every seat.  2 players: a game that ends by score (id 400) and one that runs into the
+            # 100-round cap on its own (id 401; found with the oracle).  3 and 4 players: turn counters preset to 95 (pad).
+            for PP, seat, g, pad in ((2, 0, 400, 0), (2, 1, 401, 0), (2, 0, 402, 0), (3, 1, 403, 95), (4, 3, 404, 95), (4, 0, 405, 95)):
+                eps.append(record_episode(PP, seat, seed, g, "scripted", "scripted", False, pad=pad))
         else:
             for seat in range(P):  # game ids of one seat are contiguous: SplendorVecEnv(fixed_turn=seat, first_game=..) replays them
                 for k in range(per_seat):

@@ -72,7 +72,7 @@ def load_env_episodes(name):
             opponents=str(d["opponents"][g]), decks=d["decks"][g], nobles=d["nobles"][g][:P + 1], action=d["action"][lo:hi],
             reward=d["reward"][lo:hi], terminated=d["terminated"][lo:hi], obs=d["obs"][lo:hi], snap=d["snap"][lo:hi],
             legal=[d["legal_flat"][legal_off[i]:legal_off[i + 1]] for i in range(lo, hi)],
-            all_actions=d["all_actions"][all_off[g]:all_off[g + 1]],
+            all_actions=d["all_actions"][all_off[g]:all_off[g + 1]], pad=int(d["pad"][g]) if "pad" in d else 0,
         ))
     return eps
 

@@ -43,6 +43,9 @@ def test_oracle_env_emulation_matches_reference_env(oracle, name):
             else:
                 assert ep["action"][c] == -1 and ep["reward"][c] == 0
             opponents_until_learner(oracle, s, ep, log)
+            if c == 0 and ep["pad"]:  # turn counters preset right after reset (see gen_golden_env.py)
+                for i in range(ep["P"]):
+                    s.pl[i].turns += ep["pad"]
             assert (oracle.game_ends(s, True) != 0) == bool(ep["terminated"][c]), where
             assert np.array_equal(s.snapshot(), ep["snap"][c]), where
             assert np.array_equal(oracle.legal(s, ep["my_id"]), ep["legal"][c]), where

@@ -27,6 +27,12 @@ def snaps(eng, pkg):
     return pkg.state.snapshots(eng.state_numpy(), eng.P)
 
 
+def add_turns(eng, P, pad):
+    """Preset every seat's turn counter (+pad): bits 0..15 of word 3 of each player's chunk (include/splendor_b200.h)."""
+    for p in range(P):
+        eng.state[2 + p, :, 3] += pad
+
+
 def nobles5(eps):
     return np.stack([np.concatenate([e["nobles"], [255] * (5 - len(e["nobles"]))]) for e in eps]).astype(np.uint8)
 
@@ -112,9 +118,15 @@ def test_self_play_replay_of_scripted_episodes_reaches_the_round_cap(pkg):
                 assert np.array_equal(obs.view(np.uint32), e["obs"][call].view(np.uint32)), (gi, call)
             call += 1
 
+        acts = [int(a) for a in e["all_actions"]]
+        if e["pad"]:  # opponents seated before the learner move first, then the turn counters are preset
+            for a in acts[:me]:
+                eng.env_step(None, torch.tensor([a], dtype=torch.int16), self_play=True, want_mask=False, want_obs=False)
+            acts = acts[me:]
+            add_turns(eng, P, e["pad"])
         obs, _, term, _, mask = (x.cpu().numpy() for x in eng.env_step(None, torch.tensor([-1], dtype=torch.int16), self_play=True))
         at_call_boundary(obs[0], mask[0], term[0])
-        for a in e["all_actions"]:
+        for a in acts:
             assert not term[0]
             obs, _, term, illegal, mask = (x.cpu().numpy() for x in eng.env_step(None, torch.tensor([int(a)], dtype=torch.int16), self_play=True))
             assert illegal[0] == 0
@@ -139,6 +151,13 @@ def test_dropin_env_class_replays_scripted_episodes(pkg, monkeypatch):
         env = pkg.SplendorEnv([ScriptedAgent(0) for _ in range(P - 1)], shuffle_turns=False, fixed_turn=e["my_id"])
         obs, info = env.reset()
         assert info == {"my_id": e["my_id"]}
+        if e["pad"]:
+            st = env.state
+            for p in range(P):
+                st._words[8 + 4 * p + 3] += np.uint32(e["pad"])
+                st._traces[p].action_reward.extend([({"type": "pass", "noble": None}, 0)] * e["pad"])
+            st._refresh()
+            obs = env._vectorize(st, env.my_turn)
         for c in range(len(e["action"])):
             if c > 0:
                 obs, reward, terminated, truncated, _ = env.step(int(e["action"][c]))
