@@ -711,24 +711,43 @@ __device__ __forceinline__ int count_legal(const Env<P> &e, const Tables &T, con
     return f.res + f.same + f.diff + f.bres + f.bav;
 }
 
-// k-th legal action in ascending ALL_ACTIONS order (k < total; total == 0 means only passes are legal, k < nS)
+// The four action families in ascending ALL_ACTIONS order (pass | reserve | collect_same + collect_diff | buy_reserve +
+// buy_available).  A random choice k among `total` legal actions falls into one family; kf is its rank inside it.
+enum Family { FAM_PASS = 0, FAM_RESERVE = 1, FAM_COLLECT = 2, FAM_BUY = 3 };
+__device__ __forceinline__ int family_of_k(const Ctx &c, const FamilyCounts &f, int total, int k, int &kf)
+{
+    SPL_CHECK(k >= 0 && k < (total ? total : c.nS));
+    kf = k;
+    if (total == 0) return FAM_PASS;  // pass (:570-574) is legal only when nothing else is; k < nS picks the noble
+    if (k < f.res) return FAM_RESERVE;
+    kf = k - f.res;
+    if (kf < f.same + f.diff) return FAM_COLLECT;
+    kf -= f.same + f.diff;
+    return FAM_BUY;
+}
+
+// The kf-th legal action (ascending ALL_ACTIONS order) of family `fam`.  Reads of c / f per family:
+//   pass     -
+//   reserve  c.nS c.S c.occ c.bank_yellow c.hold c.h1
+//   collect  c.nS c.S c.hold c.h1 c.h2 c.h3, f.grp
+//   buy      c.S c.near c.gems c.cards c.yellow c.resv, f.buy, e.d
+// so a caller that knows the family at compile time (the playout kernel's second phase, where a warp holds games of one
+// family) only has to provide those.
 template <int P>
-__device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, const Ctx &c, const FamilyCounts &f,
-                                             int total, int k, Choice &ch)
+__device__ __forceinline__ void select_family(const Env<P> &e, const Tables &T, const Ctx &c, const FamilyCounts &f, int fam, int k,
+                                              Choice &ch)
 {
     ch.C = 0; ch.R = 0; ch.info = 0; ch.slot = 0;
-    SPL_CHECK(k >= 0 && k < (total ? total : c.nS));
     // Every family ends the same way - pick the pj-th set bit of a mask (board slot / return variant), pick the ni-th
     // noble of a set, index = base + n * nmul + pos * pmul - so the families only prepare those operands and the picks
-    // run ONCE for the whole warp after the branches have rejoined (a warp almost always holds lanes of every family;
-    // code inside the branches is paid once per family, code after them once).
+    // run ONCE after the branches have rejoined.
     uint32_t pm = 1u, Sb = c.S;
     int pj = 0, ni = 0, base = 0, nmul = 1, pmul = 0;
     const uint32_t *row = T.ret_same;  // collect families: returned gems of variant `pos`; others: not read
-    if (total == 0) {  // pass (:570-574): index = noble slot
+    if (fam == FAM_PASS) {  // pass (:570-574): index = noble slot
         ch.type = T_PASS;
         ni = k;
-    } else if (k < f.res) {  // reserve: index 6 + p*42 + n*7 + v
+    } else if (fam == FAM_RESERVE) {  // reserve: index 6 + p*42 + n*7 + v
         const int nv = reserve_variants(c), per = c.nS * nv;
         const int q = small_div(T, k, per), rem = k - q * per;
         ni = small_div(T, rem, nv);
@@ -745,13 +764,12 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
             }
         }
         base = BASE_RESERVE + v; nmul = 7; pmul = 42;
-    } else if (k - f.res < f.same + f.diff) {
+    } else if (fam == FAM_COLLECT) {
         // collect_same (510 + c*126 + n*21 + v) and collect_diff (combo_base + n*V + v).  The 30 groups (colours, then
         // colour combinations) lie in index order in f.grp, one byte of return-variant count each; a group holds
         // variants * nS consecutive legal actions.  Find the group of action k in two prefix-sum steps - the word, then
         // the byte inside it (a multiply by 0x01010101 turns four counts into their four running sums) - then the noble
         // slot and the vi-th payable return variant of the group's table row.
-        k -= f.res;
         const uint32_t q = (uint32_t)small_div(T, k, c.nS);
         uint32_t W = f.grp[0], before = 0, run = 0;
         int wi = 0;
@@ -791,7 +809,6 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
     } else {
         // buys: reserved cards first (3420 + r*6 + n), then the board (3438 + p*6 + n).  The card of action k by the same
         // two prefix-sum steps as the collect groups (word, then byte); what is left of k is the noble choice
-        k -= f.res + f.same + f.diff;
         uint32_t W = f.buy[0], before = 0, run = 0;
         int wi = 0;
 #pragma unroll
@@ -822,6 +839,16 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
     ch.idx = base + ch.n * nmul + pos * pmul;
     if (ch.type == T_RESERVE) ch.slot = pos;
     if (pmul == 1) { SPL_CHECK(pos < nmul); ch.R = row[pos]; }
+}
+
+// k-th legal action in ascending ALL_ACTIONS order (k < total; total == 0 means only passes are legal, k < nS)
+template <int P>
+__device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, const Ctx &c, const FamilyCounts &f,
+                                             int total, int k, Choice &ch)
+{
+    int kf;
+    const int fam = family_of_k(c, f, total, k, kf);
+    select_family(e, T, c, f, fam, kf, ch);
 }
 
 // Is ALL_ACTIONS[idx] legal for the seat to move?  Decodes it into ch either way (build_action, gym/envs/utils.py:43-145).

@@ -201,6 +201,258 @@ __global__ void __launch_bounds__(BLOCK, SPL_PLAYOUT_MINBLOCKS) playout_kernel(c
     if (a.counters && threadIdx.x < 16 && sctr[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], sctr[threadIdx.x]);
 }
 
+// ---------------------------------------------------------------------------------------------- playout, block pools
+// GAMES LIVE IN SHARED MEMORY, WARPS ARE WORKERS.  A block owns a pool of up to CAP = 32 * NW games (packed state words
+// in shared memory, 64 B per 2-player game) and plays them in ROUNDS: one round = one move of every live game of the pool.
+//   phase A  warp w takes the w-th group of 32 live games (always full except the last group): load the state, terminal
+//            context, the legal COUNTS of all four action families, the Philox draw -> (family, rank inside the family);
+//            the game gets a slot in the family-sorted list (warp-aggregated shared-memory atomics), and - after a block
+//            barrier, when the family totals are known - writes its state, (family, rank, context bits) and the family's
+//            count words there;
+//   phase B  warp w takes the w-th group of 32 entries of the SORTED list: every lane of the warp (except in the at most
+//            three groups that straddle a family boundary) holds a game of the SAME family, so the family-specific
+//            selection and the apply run without divergence; the survivors are appended to the next round's live list,
+//            finished games are scored and written out;
+//   refill   whenever 32 slots are free a spare warp starts 32 new games (reset / load) with all lanes active.
+// This removes the two losses the one-game-per-thread kernel measured (profiles/r1q_playout.md): 24 of 32 lanes alive
+// (a warp waited for its longest game) and the ~470 instructions per step that every warp executed inside family branches
+// at ~8 lanes.  Decks are drawn lazily from the counter-based form (a deal is one Philox call + a bit select, now at full
+// lanes inside a reserve / buy group), so nothing but the 16-24 state words per game has to live on chip.
+// Results do not depend on where a game sits: every random draw is keyed by (seed, game id, turn / draw number).
+#ifndef SPL_POOL_WARPS
+#define SPL_POOL_WARPS 10
+#endif
+#ifndef SPL_POOL_BLOCKS_PER_SM
+#define SPL_POOL_BLOCKS_PER_SM 2
+#endif
+constexpr int POOL_PASS_WORDS = 11;  // header (2) + the collect family's nine group-count words
+
+template <int P, int NW>
+struct PoolSmem {
+    static constexpr int CAP = 32 * NW, C = 2 + P;
+    uint4 st[2][C][CAP];                // [0] live list of the round, [1] family-sorted list; chunk-major like the HBM layout
+    uint32_t gid[2][CAP];               // game index inside the launch
+    uint32_t t0[2][CAP];                // total turns when the game entered the pool (0 for fresh games)
+    uint32_t pw[POOL_PASS_WORDS][CAP];  // phase A -> phase B words, at sorted positions
+    Tables T;
+    unsigned long long ctr[16];
+    int n_alive[2];
+    int fam_cnt[2][4];
+};
+
+enum PoolMode { POOL_FRESH = 0, POOL_STATES = 1 };
+
+template <int P, int NW>
+__device__ __forceinline__ void pool_load(Env<P> &e, const uint4 (*st)[PoolSmem<P, NW>::CAP], int p)
+{
+    const uint4 a = st[0][p], b = st[1][p];
+    e.bank = a.x; e.d[0] = a.y; e.d[1] = a.z; e.d[2] = a.w;
+    e.k[0] = b.x; e.k[1] = b.y; e.k[2] = b.z; e.meta = b.w;
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+        const uint4 v = st[2 + q][p];
+        e.pg[q] = v.x; e.pc[q] = v.y; e.pr[q] = v.z; e.pi[q] = v.w;
+    }
+}
+template <int P, int NW>
+__device__ __forceinline__ void pool_store(const Env<P> &e, uint4 (*st)[PoolSmem<P, NW>::CAP], int p)
+{
+    st[0][p] = make_uint4(e.bank, e.d[0], e.d[1], e.d[2]);
+    st[1][p] = make_uint4(e.k[0], e.k[1], e.k[2], e.meta);
+#pragma unroll
+    for (int q = 0; q < P; q++) st[2 + q][p] = make_uint4(e.pg[q], e.pc[q], e.pr[q], e.pi[q]);
+}
+
+// a finished game: calScore, win / tie / loss, counters (block-level, shared memory), per-game outputs
+template <int P>
+__device__ __forceinline__ void pool_finalize(const Env<P> &e, const PlayoutArgs &a, unsigned long long *sctr, int64_t g, int steps, int kind)
+{
+    int sc[P], oc[P];
+    final_scores(e, sc, oc);
+    unsigned long long nob = 0, sum = 0;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        if (a.score2) a.score2[g * P + p] = (int8_t)sc[p];
+        if (oc[p] == 2) atomicAdd(&sctr[SPL_CTR_WINS + p], 1ull);
+        if (oc[p] == 1) atomicAdd(&sctr[SPL_CTR_TIES + p], 1ull);
+        sum += (unsigned)sc[p];
+        nob += __popc(e.pi[p] >> 16 & 0x3FFu);
+    }
+    atomicAdd(&sctr[SPL_CTR_GAMES], 1ull);
+    atomicAdd(&sctr[SPL_CTR_STEPS], (unsigned long long)steps);
+    atomicAdd(&sctr[SPL_CTR_END_SCORE - 1 + kind], 1ull);
+    atomicAdd(&sctr[SPL_CTR_SCORE2_SUM], sum);
+    atomicAdd(&sctr[SPL_CTR_NOBLES], nob);
+    if (a.steps) a.steps[g] = (int16_t)steps;
+    if (a.end_kind) a.end_kind[g] = (uint8_t)kind;
+    if (a.state) store_env(e, a.state, a.n_games, g);
+}
+
+// slot of this lane in a shared list: lanes with `want` take consecutive slots starting at the counter's old value
+__device__ __forceinline__ int pool_append(int *counter, bool want, int lane)
+{
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+    int base = 0;
+    if (m && lane == __ffs(m) - 1) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, m ? __ffs(m) - 1 : 0);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
+template <int P, int MODE, int NW>
+__global__ void __launch_bounds__(32 * NW, SPL_POOL_BLOCKS_PER_SM) playout_pool_kernel(const __grid_constant__ PlayoutArgs a)
+{
+    using Sm = PoolSmem<P, NW>;
+    constexpr int CAP = Sm::CAP;
+    extern __shared__ __align__(16) unsigned char pool_raw[];
+    Sm &S = *reinterpret_cast<Sm *>(pool_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 16) S.ctr[threadIdx.x] = 0;
+    if (threadIdx.x < 2) S.n_alive[threadIdx.x] = 0;
+    if (threadIdx.x < 8) S.fam_cnt[threadIdx.x >> 2][threadIdx.x & 3] = 0;
+    stage_tables(S.T);  // ends with a block barrier
+    const Tables &T = S.T;
+
+    // the launch's games are split evenly over the blocks; a block starts them as slots of its pool come free
+    const int64_t g_hi = a.n_games * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    int64_t next = a.n_games * (int64_t)blockIdx.x / gridDim.x;
+
+    for (int round = 0;; round++) {
+        const int b = round & 1;
+        const int nA = S.n_alive[b];
+        const int chunks = (nA + 31) >> 5;
+        const int64_t left = g_hi - next;
+        int n_new = min(NW - chunks, (CAP - nA) >> 5);
+        n_new = (int)min((int64_t)n_new, (left + 31) >> 5);
+        if (chunks == 0 && n_new == 0) break;
+        const bool stepper = warp < chunks;
+        const int p = warp * 32 + lane;
+        const bool valid = stepper && p < nA;
+        const int64_t g_new = next + (int64_t)(warp - chunks) * 32 + lane;
+        const bool loading = !stepper && warp - chunks < n_new && g_new < g_hi;
+
+        Env<P> e;
+        uint32_t gid = 0, t0 = 0, w0 = 0, w1 = 0, w2 = 0;
+        FamilyCounts f;
+        int fam = 4, rank = 0;
+        bool fresh_alive = false;
+        // ------------------------------------------------------------------ phase A (and the loading of new games)
+        if (valid) {
+            pool_load<P, NW>(e, S.st[0], p);
+            gid = S.gid[0][p]; t0 = S.t0[0][p];
+            const uint64_t game = (MODE == POOL_STATES && a.game_ids) ? a.game_ids[gid] : a.first_game + gid;
+            const uint32_t r = philox_rk(a.rk, game, turns_total(e), STREAM_ACTION).x;
+            Ctx c;
+            make_ctx(e, T, c);
+            const int total = count_legal(e, T, c, f);
+            int kf;
+            fam = family_of_k(c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), kf);
+            w0 = (uint32_t)kf | (uint32_t)fam << 13 | c.S << 15 | (uint32_t)c.hold << 20 | (c.bank_yellow ? 1u << 24 : 0u);
+            w1 = c.h1 | c.h2 << 6 | c.h3 << 12 | c.occ << 18;
+            w2 = c.near;
+        } else if (loading) {
+            gid = (uint32_t)g_new;
+            if (MODE == POOL_FRESH) {
+                reset_env(e, a.seed, a.first_game + (uint64_t)g_new, a.rk);
+                fresh_alive = true;
+            } else {
+                load_env(e, a.state, a.n_games, g_new);
+                t0 = turns_total(e);
+                const int kind0 = game_ends(e, a.flags);
+                fresh_alive = kind0 == SPL_END_NONE;
+                if (!fresh_alive) pool_finalize(e, a, S.ctr, g_new, 0, kind0);  // the game was over when it was handed in
+            }
+        }
+        if (stepper) {  // slot inside the family (all 32 lanes take part; lanes beyond the list carry fam == 4)
+#pragma unroll
+            for (int F = 0; F < 4; F++) {
+                const int slot = pool_append(&S.fam_cnt[b][F], fam == F, lane);
+                if (fam == F) rank = slot;
+            }
+        }
+        __syncthreads();  // ---- barrier 1: family totals are final; every read of the live list st[0] is done
+        if (threadIdx.x == 0) {
+            S.n_alive[b] = 0;  // this round's count has been read by everybody; it is the next round's append counter
+#pragma unroll
+            for (int F = 0; F < 4; F++) S.fam_cnt[b ^ 1][F] = 0;
+        }
+        if (valid) {
+            int base = 0;
+#pragma unroll
+            for (int F = 0; F < 3; F++) base += fam > F ? S.fam_cnt[b][F] : 0;
+            const int q = base + rank;
+            pool_store<P, NW>(e, S.st[1], q);
+            S.gid[1][q] = gid; S.t0[1][q] = t0;
+            S.pw[0][q] = w0; S.pw[1][q] = w1;
+            if (fam == FAM_COLLECT) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) S.pw[2 + i][q] = f.grp[i];
+            } else if (fam == FAM_BUY) {
+                S.pw[2][q] = w2;
+#pragma unroll
+                for (int i = 0; i < 4; i++) S.pw[3 + i][q] = f.buy[i];
+            }
+        }
+        __syncthreads();  // ---- barrier 2: the sorted list is complete
+        // ------------------------------------------------------------------ phase B
+        bool survive = fresh_alive;
+        int kind = SPL_END_NONE, t = 0;
+        if (valid) {
+            pool_load<P, NW>(e, S.st[1], p);
+            gid = S.gid[1][p]; t0 = S.t0[1][p];
+            w0 = S.pw[0][p]; w1 = S.pw[1][p];
+            fam = (int)(w0 >> 13 & 3u);
+            const int kf = (int)(w0 & 0x1FFFu);
+            const uint64_t game = (MODE == POOL_STATES && a.game_ids) ? a.game_ids[gid] : a.first_game + gid;
+            const DeckSrc src{(MODE == POOL_STATES && a.decks) ? a.decks + (int64_t)gid * SPL_DECK_BYTES : nullptr, a.seed, game, a.rk};
+            Ctx c;
+            const int seat = seat_of(e.meta);
+            c.gems = e.pg[0]; c.cards = e.pc[0]; c.resv = e.pr[0];
+#pragma unroll
+            for (int q = 1; q < P; q++)
+                if (seat == q) { c.gems = e.pg[q]; c.cards = e.pc[q]; c.resv = e.pr[q]; }
+            c.bank = e.bank;
+            c.S = w0 >> 15 & 31u; c.nS = c.S ? __popc(c.S) : 1;
+            c.hold = (int)(w0 >> 20 & 15u); c.bank_yellow = w0 >> 24 & 1u;
+            c.h1 = w1 & 63u; c.h2 = w1 >> 6 & 63u; c.h3 = w1 >> 12 & 63u; c.occ = w1 >> 18;
+            c.yellow = (int)field(c.gems, YSH);
+            c.near = 0;
+            Choice ch;
+            if (fam == FAM_COLLECT) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) f.grp[i] = S.pw[2 + i][p];
+                select_family(e, T, c, f, FAM_COLLECT, kf, ch);
+            } else if (fam == FAM_RESERVE) {
+                select_family(e, T, c, f, FAM_RESERVE, kf, ch);
+            } else if (fam == FAM_BUY) {
+                c.near = S.pw[2][p];
+#pragma unroll
+                for (int i = 0; i < 4; i++) f.buy[i] = S.pw[3 + i][p];
+                select_family(e, T, c, f, FAM_BUY, kf, ch);
+            } else {
+                select_family(e, T, c, f, FAM_PASS, kf, ch);
+            }
+            t = (int)turns_total(e);
+            if (__builtin_expect(t < a.trace_len, 0)) a.trace[(int64_t)t * a.n_games + gid] = (int16_t)ch.idx;
+            apply_action<P, false>(e, ch, src);
+            t++;
+            kind = game_ends(e, a.flags);
+            if (kind == SPL_END_NONE && t - (int)t0 >= a.max_steps) kind = SPL_END_TRUNCATED;
+            survive = kind == SPL_END_NONE;
+        }
+        if (stepper || n_new) {  // warp-uniform: the stepping warps and (when games are being started) the others
+            const int q = pool_append(&S.n_alive[b ^ 1], survive, lane);
+            if (survive) {
+                pool_store<P, NW>(e, S.st[0], q);
+                S.gid[0][q] = gid; S.t0[0][q] = t0;
+            }
+        }
+        if (valid && !survive) pool_finalize(e, a, S.ctr, (int64_t)gid, t - (int)t0, kind);
+        next = min(g_hi, next + (int64_t)n_new * 32);
+        __syncthreads();  // ---- barrier 3: the next round's live list is complete
+    }
+    if (a.counters && threadIdx.x < 16 && S.ctr[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], S.ctr[threadIdx.x]);
+}
+
 // ---------------------------------------------------------------------------------------------- step
 template <int P>
 __global__ void __launch_bounds__(BLOCK) step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
@@ -746,6 +998,27 @@ static int resident_blocks(size_t dyn_bytes)  // per SM, by shared memory (227 K
     default: return SPL_E_BADARG;      \
     }
 
+template <int P, int MODE>
+static int launch_pool(const PlayoutArgs &a, cudaStream_t stream)
+{
+    constexpr int NW = SPL_POOL_WARPS;
+    using Sm = PoolSmem<P, NW>;
+    auto kernel = playout_pool_kernel<P, MODE, NW>;
+    static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 16 && !configured[dev]) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sm)));
+        configured[dev] = true;
+    } else if (dev >= 16) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sm)));
+    }
+    const int64_t cap = (int64_t)sm_count() * SPL_POOL_BLOCKS_PER_SM, want = (a.n_games + 31) / 32;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    kernel<<<grid, 32 * NW, sizeof(Sm), stream>>>(a);
+    return SPL_OK;
+}
+
 extern "C" {
 
 int spl_abi_version(void) { return 1; }
@@ -941,15 +1214,23 @@ static int launch_playout(bool fresh, const PlayoutArgs &args, int P, cudaStream
     if (!a.trace) a.trace_len = 0;  // the kernel tests trace_len only
     if (a.trace && a.trace_len > 0)
         CK(cudaMemsetAsync(a.trace, 0xFF, (size_t)a.trace_len * (size_t)a.n_games * sizeof(int16_t), stream));
+    static int impl = -1;
+    if (impl < 0) {  // SPL_PLAYOUT_IMPL=thread: the one-game-per-thread kernel (A/B only)
+        const char *s = getenv("SPL_PLAYOUT_IMPL");
+        impl = (s && !strcmp(s, "thread")) ? 1 : 0;
+    }
+    if (impl == 0) {
+        if (fresh) { DISPATCH_P(P, if (int rc = launch_pool<PP, POOL_FRESH>(a, stream)) return rc); }
+        else { DISPATCH_P(P, if (int rc = launch_pool<PP, POOL_STATES>(a, stream)) return rc); }
+        CK(cudaGetLastError());
+        return SPL_OK;
+    }
     static int blk = 0;
     if (!blk) {  // SPL_PLAYOUT_BLOCK: threads per block (32, 64, 96 or 128) - a tuning knob, see profiles/r1_playout_ncu.md
         const char *s = getenv("SPL_PLAYOUT_BLOCK");
         blk = s ? atoi(s) : PLAYOUT_BLOCK;
         if (blk != 32 && blk != 64 && blk != 96 && blk != 128) blk = PLAYOUT_BLOCK;
     }
-    // One instantiation per player count.  Up to r1n a second, register-lean one (rolled buy loop, 72 registers, 7 blocks
-    // per SM) won on launches of >= 2^20 games; after the r1o-r1q rewrite of the step it spills and is 6 % slower there
-    // (profiles/r1q_playout.md), so it was removed.
     const unsigned grid = (unsigned)((a.n_games + blk - 1) / blk);
     if (fresh) { DISPATCH_P(P, playout_kernel<PP, true><<<grid, blk, 0, stream>>>(a)); }
     else { DISPATCH_P(P, playout_kernel<PP, false><<<grid, blk, 0, stream>>>(a)); }
