@@ -51,7 +51,7 @@ __host__ __device__ constexpr int field_of_colour_id(int c) { return c == 5 ? 2 
 enum ActType { T_PASS = 0, T_RESERVE = 1, T_SAME = 2, T_DIFF = 3, T_BUY_RESERVE = 4, T_BUY_AVAILABLE = 5 };
 constexpr int BASE_RESERVE = 6, BASE_SAME = 510, BASE_DIFF = 1140, BASE_BUY_RESERVE = 3420, BASE_BUY_AVAILABLE = 3438;
 
-struct Tables {
+struct alignas(16) Tables {
     uint2 card[128];         // .x = cost (g6, yellow field 0) ; .y = 5*colour_field | points << 5 | tier << 8;
                              // entries 90..127 (an empty slot's 0xFF & 127 lands on 127): colour shift = yellow, never buyable
     uint32_t noble[16];      // requirement (g6); entry 15 = "no noble" (unsatisfiable)

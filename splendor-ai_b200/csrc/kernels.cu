@@ -29,10 +29,6 @@ __device__ const Tables g_tables = make_tables();
 __device__ const uint32_t g_log1p_bits[32] = SPL_LOG1P_BITS;
 
 constexpr int BLOCK = 128;
-constexpr int PLAYOUT_BLOCK = 128;  // default threads per block of the playout kernel
-#ifndef SPL_PLAYOUT_MINBLOCKS
-#define SPL_PLAYOUT_MINBLOCKS 5  // resident 128-thread blocks per SM the playout kernel is compiled for (register cap)
-#endif
 
 __device__ __forceinline__ void stage_tables(Tables &sT)
 {
@@ -42,6 +38,19 @@ __device__ __forceinline__ void stage_tables(Tables &sT)
     __syncthreads();
 }
 static_assert(sizeof(Tables) % 4 == 0, "Tables must be word-copyable");
+// The same copy for the persistent thread-per-env kernels, WITHOUT the barrier: the caller issues its first env's loads,
+// calls this (every thread has a few independent 16-byte loads in flight), then synchronises - the table copy and the
+// state loads overlap instead of forming a serial prologue.
+__device__ __forceinline__ void stage_tables_nosync(Tables &sT)
+{
+    static_assert(sizeof(Tables) % 16 == 0 && alignof(Tables) >= 16, "Tables must be copyable in 16-byte pieces");
+    const uint4 *src = reinterpret_cast<const uint4 *>(&g_tables);
+    uint4 *dst = reinterpret_cast<uint4 *>(&sT);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 16); i += blockDim.x) dst[i] = src[i];
+}
+constexpr int ENV_TB = 256;        // threads per block of the persistent thread-per-env kernels (step, env move)
+constexpr int STEP_BLOCKS_PER_SM = 4, ENV_MOVE_BLOCKS_PER_SM = 3;  // what the register counts (64 / 80) let reside
 
 // ---------------------------------------------------------------------------------------------- reset / inject
 template <int P>
@@ -70,19 +79,17 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(uint4 *state, uint64_t see
     }
 }
 
+// BoardState.__init__ from caller-supplied deck orders and nobles: what the 12 initial deals leave (explicit-list deck form)
 template <int P>
-__global__ void __launch_bounds__(BLOCK) inject_kernel(uint4 *state, const uint8_t *deck_lists, const uint8_t *nobles, int64_t N)
+__device__ __forceinline__ void inject_env(Env<P> &e, const uint8_t *lists, const uint8_t *nobles)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    Env<P> e;
     const uint32_t n = P == 2 ? 4 : (P == 3 ? 5 : 7);
     e.bank = n * (ONES6 & ~(1u << YSH)) | (5u << YSH);
     e.k[0] = 40u | 30u << 8 | 20u << 16; e.k[1] = 0; e.k[2] = 0;
     uint32_t list = 0xFFFFFu;
-    for (int k = 0; k < P + 1; k++) list = (list & ~(15u << (4 * k))) | ((uint32_t)(nobles[i * 5 + k] & 15u) << (4 * k));
+    for (int k = 0; k < P + 1; k++) list = (list & ~(15u << (4 * k))) | ((uint32_t)(nobles[k] & 15u) << (4 * k));
     e.meta = list | ((uint32_t)(P - 2) << 22) | META_EXPLICIT;
-    const DeckSrc src{deck_lists + i * SPL_DECK_BYTES, 0, 0};
+    const DeckSrc src{lists, 0, 0};
 #pragma unroll
     for (int t = 0; t < 3; t++) {
         uint32_t w = 0;
@@ -92,13 +99,23 @@ __global__ void __launch_bounds__(BLOCK) inject_kernel(uint4 *state, const uint8
     }
 #pragma unroll
     for (int p = 0; p < P; p++) { e.pg[p] = 0; e.pc[p] = 0; e.pr[p] = 0x00FFFFFFu; e.pi[p] = 0; }
+}
+
+template <int P>
+__global__ void __launch_bounds__(BLOCK) inject_kernel(uint4 *state, const uint8_t *deck_lists, const uint8_t *nobles, int64_t N)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Env<P> e;
+    inject_env(e, deck_lists + i * SPL_DECK_BYTES, nobles + i * 5);
     store_env(e, state, N, i);
 }
 
 // ---------------------------------------------------------------------------------------------- playout
 struct PlayoutArgs {
     uint4 *state;           // FRESH: optional final-state output; else in/out states
-    const uint8_t *decks;   // explicit deck lists (only with states) or nullptr
+    const uint8_t *decks;   // explicit deck lists (only with states / POOL_LISTS) or nullptr
+    const uint8_t *nobles;  // POOL_LISTS: noble ids, 5 bytes per game
     uint64_t seed, first_game;
     const uint64_t *game_ids;  // per-game ids (only with states) or nullptr = first_game + index
     int64_t n_games;
@@ -122,125 +139,42 @@ __device__ __forceinline__ uint32_t turns_total(const Env<P> &e)
     return t;
 }
 
-// ONE GAME PER THREAD, one launch = n_games threads in blocks of `blk`.  The hardware block scheduler is the refill
-// mechanism: as soon as the slowest game of a block ends, a fresh block takes its place, so every SM always holds as
-// many games as its registers allow, and the 32 games of a warp stay in the same phase (reset together, step together,
-// score together).  An earlier persistent form (lanes drew their next game themselves) left each lane of a warp in a
-// different phase - reset / finalize ran one lane at a time and the instruction cache thrashed - and was 25-40 % slower
-// on large sweeps (profiles/r1_playout_ncu.md).
-template <int P, bool FRESH>
-__global__ void __launch_bounds__(BLOCK, SPL_PLAYOUT_MINBLOCKS) playout_kernel(const __grid_constant__ PlayoutArgs a)  // 92 registers
-{
-    __shared__ Tables sT;
-    __shared__ unsigned long long sctr[16];
-    // FRESH: every game's whole deck order, drawn at reset (reset_env_lists); 92-byte pitch = 23 words, odd, so the 32
-    // lanes of a warp writing the same entry hit 32 different banks
-    constexpr int LIST_PITCH = 92;
-    __shared__ __align__(4) uint8_t s_lists[FRESH ? BLOCK * LIST_PITCH : 4];
-    if (threadIdx.x < 16) sctr[threadIdx.x] = 0;
-    stage_tables(sT);
-
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = g < a.n_games;
-    uint8_t *const my_lists = s_lists + (FRESH ? threadIdx.x * LIST_PITCH : 0);
-    Env<P> e;
-    int t = 0, kind = SPL_END_NONE;
-    if (live) {
-        DeckSrc src{nullptr, a.seed, (!FRESH && a.game_ids) ? a.game_ids[g] : a.first_game + (uint64_t)g, a.rk};
-        if (FRESH) {
-            reset_env_lists(e, a.seed, src.game, a.rk, my_lists);
-            src.lists = my_lists;
-        } else {
-            load_env(e, a.state, a.n_games, g);
-            src.lists = a.decks ? a.decks + g * SPL_DECK_BYTES : nullptr;
-        }
-        t = (int)turns_total(e);
-        const int t_end = t + a.max_steps;
-        for (;;) {
-            kind = game_ends(e, a.flags);
-            if (kind == SPL_END_NONE && t >= t_end) kind = SPL_END_TRUNCATED;
-            if (kind != SPL_END_NONE) break;
-            Ctx c;
-            FamilyCounts f;
-            Choice ch;
-            const uint32_t r = philox_rk(a.rk, src.game, (uint32_t)t, STREAM_ACTION).x;
-            make_ctx(e, sT, c);
-            const int total = count_legal(e, sT, c, f);
-            select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
-            if (__builtin_expect(t < a.trace_len, 0)) a.trace[(int64_t)t * a.n_games + g] = (int16_t)ch.idx;  // trace_len is 0 without a trace
-            apply_action<P, FRESH>(e, ch, src);
-            t++;
-        }
-    }
-    // the warp is back together: calScore, win/tie/loss, counters, outputs
-    if (live) {
-        int sc[P], oc[P];
-        final_scores(e, sc, oc);
-        unsigned long long nob = 0, sum = 0;
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-            if (a.score2) a.score2[g * P + p] = (int8_t)sc[p];
-            if (oc[p] == 2) atomicAdd(&sctr[SPL_CTR_WINS + p], 1ull);
-            if (oc[p] == 1) atomicAdd(&sctr[SPL_CTR_TIES + p], 1ull);
-            sum += (unsigned)sc[p];
-            nob += __popc(e.pi[p] >> 16 & 0x3FFu);
-        }
-        atomicAdd(&sctr[SPL_CTR_GAMES], 1ull);
-        atomicAdd(&sctr[SPL_CTR_STEPS], (unsigned long long)t);
-        atomicAdd(&sctr[SPL_CTR_END_SCORE - 1 + kind], 1ull);
-        atomicAdd(&sctr[SPL_CTR_SCORE2_SUM], sum);
-        atomicAdd(&sctr[SPL_CTR_NOBLES], nob);
-        if (a.steps) a.steps[g] = (int16_t)t;
-        if (a.end_kind) a.end_kind[g] = (uint8_t)kind;
-        if (a.state) {
-            if (FRESH) lists_to_masks(e, my_lists);  // back to the counter-based deck form of the ABI
-            store_env(e, a.state, a.n_games, g);
-        }
-    }
-    __syncthreads();
-    if (a.counters && threadIdx.x < 16 && sctr[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], sctr[threadIdx.x]);
-}
-
 // ---------------------------------------------------------------------------------------------- playout, block pools
-// GAMES LIVE IN SHARED MEMORY, WARPS ARE WORKERS.  A block owns a pool of up to CAP = 32 * NW games (packed state words
-// in shared memory, 64 B per 2-player game) and plays them in ROUNDS: one round = one move of every live game of the pool.
-//   phase A  warp w takes the w-th group of 32 live games (always full except the last group): load the state, terminal
-//            context, the legal COUNTS of all four action families, the Philox draw -> (family, rank inside the family);
-//            the game gets a slot in the family-sorted list (warp-aggregated shared-memory atomics), and - after a block
-//            barrier, when the family totals are known - writes its state, (family, rank, context bits) and the family's
-//            count words there;
-//   phase B  warp w takes the w-th group of 32 entries of the SORTED list: every lane of the warp (except in the at most
-//            three groups that straddle a family boundary) holds a game of the SAME family, so the family-specific
-//            selection and the apply run without divergence; the survivors are appended to the next round's live list,
-//            finished games are scored and written out;
-//   refill   whenever 32 slots are free a spare warp starts 32 new games (reset / load) with all lanes active.
-// This removes the two losses the one-game-per-thread kernel measured (profiles/r1q_playout.md): 24 of 32 lanes alive
-// (a warp waited for its longest game) and the ~470 instructions per step that every warp executed inside family branches
-// at ~8 lanes.  Decks are drawn lazily from the counter-based form (a deal is one Philox call + a bit select, now at full
-// lanes inside a reserve / buy group), so nothing but the 16-24 state words per game has to live on chip.
-// Results do not depend on where a game sits: every random draw is keyed by (seed, game id, turn / draw number).
+// A block owns a POOL of up to CAP = 32 * NW games.  Between rounds the live games sit in shared memory as a dense list
+// (packed state words, 64 B per 2-player game, chunk-major like the HBM layout); in a ROUND warp w loads the w-th group of
+// 32 live games into registers and plays SPL_POOL_STEPS moves of each out of registers, exactly as a one-game-per-thread
+// kernel would; the survivors are appended to the next round's list (one warp-aggregated shared-memory atomic), the games
+// that ended are scored, and whenever 32 slots are free a spare warp starts 32 new games with all lanes active.
+// So the lanes of a stepping warp are (nearly) always all alive: the one-game-per-thread kernel of round 1 kept 24 of 32
+// (a warp waited for its longest game: profiles/r1q_playout.md), which was its largest single loss.  The price is one
+// block barrier and ~60 instructions of list traffic per round, i.e. per SPL_POOL_STEPS moves.
+// A second form that also SORTED the games by action family between counting and selecting (so that a warp selects and
+// applies one family without divergence) was built first and measured slower: handing the counts from one phase to the
+// other plus two more barriers per move cost more than the ~100 divergent instructions it saved (profiles/r2_playout.md).
+// Decks are drawn lazily from the counter-based form (a deal = one Philox call + a bit select), so a game needs nothing on
+// chip but its state words.  Results do not depend on where a game sits: every draw is keyed by (seed, game id, turn).
 #ifndef SPL_POOL_WARPS
-#define SPL_POOL_WARPS 10
+#define SPL_POOL_WARPS 20
 #endif
 #ifndef SPL_POOL_BLOCKS_PER_SM
-#define SPL_POOL_BLOCKS_PER_SM 2
+#define SPL_POOL_BLOCKS_PER_SM 1
 #endif
-constexpr int POOL_PASS_WORDS = 11;  // header (2) + the collect family's nine group-count words
+#ifndef SPL_POOL_STEPS
+#define SPL_POOL_STEPS 8
+#endif
 
 template <int P, int NW>
 struct PoolSmem {
     static constexpr int CAP = 32 * NW, C = 2 + P;
-    uint4 st[2][C][CAP];                // [0] live list of the round, [1] family-sorted list; chunk-major like the HBM layout
-    uint32_t gid[2][CAP];               // game index inside the launch
-    uint32_t t0[2][CAP];                // total turns when the game entered the pool (0 for fresh games)
-    uint32_t pw[POOL_PASS_WORDS][CAP];  // phase A -> phase B words, at sorted positions
+    uint4 st[2][C][CAP];   // live list of this round / of the next round
+    uint32_t gid[2][CAP];  // game index inside the launch
+    uint32_t t0[2][CAP];   // total turns when the game entered the pool (0 for fresh games)
     Tables T;
-    unsigned long long ctr[16];
-    int n_alive[2];
-    int fam_cnt[2][4];
+    unsigned int ctr[16];  // block-level counters (32 bits are enough for one block of one launch)
+    int n_alive[3];        // list lengths, rotating: read in round r, appended to for round r+1, zeroed for round r+2
 };
 
-enum PoolMode { POOL_FRESH = 0, POOL_STATES = 1 };
+enum PoolMode { POOL_FRESH = 0, POOL_STATES = 1, POOL_LISTS = 2 };  // new games: Philox reset | states from HBM | deck orders + nobles
 
 template <int P, int NW>
 __device__ __forceinline__ void pool_load(Env<P> &e, const uint4 (*st)[PoolSmem<P, NW>::CAP], int p)
@@ -265,37 +199,26 @@ __device__ __forceinline__ void pool_store(const Env<P> &e, uint4 (*st)[PoolSmem
 
 // a finished game: calScore, win / tie / loss, counters (block-level, shared memory), per-game outputs
 template <int P>
-__device__ __forceinline__ void pool_finalize(const Env<P> &e, const PlayoutArgs &a, unsigned long long *sctr, int64_t g, int steps, int kind)
+__device__ __forceinline__ void pool_finalize(const Env<P> &e, const PlayoutArgs &a, unsigned int *sctr, int64_t g, int steps, int kind)
 {
     int sc[P], oc[P];
     final_scores(e, sc, oc);
-    unsigned long long nob = 0, sum = 0;
+    unsigned int nob = 0, sum = 0;
 #pragma unroll
     for (int p = 0; p < P; p++) {
         if (a.score2) a.score2[g * P + p] = (int8_t)sc[p];
-        if (oc[p] == 2) atomicAdd(&sctr[SPL_CTR_WINS + p], 1ull);
-        if (oc[p] == 1) atomicAdd(&sctr[SPL_CTR_TIES + p], 1ull);
+        if (oc[p]) atomicAdd(&sctr[(oc[p] == 2 ? SPL_CTR_WINS : SPL_CTR_TIES) + p], 1u);
         sum += (unsigned)sc[p];
         nob += __popc(e.pi[p] >> 16 & 0x3FFu);
     }
-    atomicAdd(&sctr[SPL_CTR_GAMES], 1ull);
-    atomicAdd(&sctr[SPL_CTR_STEPS], (unsigned long long)steps);
-    atomicAdd(&sctr[SPL_CTR_END_SCORE - 1 + kind], 1ull);
+    atomicAdd(&sctr[SPL_CTR_GAMES], 1u);
+    atomicAdd(&sctr[SPL_CTR_STEPS], (unsigned)steps);
+    atomicAdd(&sctr[SPL_CTR_END_SCORE - 1 + kind], 1u);
     atomicAdd(&sctr[SPL_CTR_SCORE2_SUM], sum);
-    atomicAdd(&sctr[SPL_CTR_NOBLES], nob);
+    if (nob) atomicAdd(&sctr[SPL_CTR_NOBLES], nob);
     if (a.steps) a.steps[g] = (int16_t)steps;
     if (a.end_kind) a.end_kind[g] = (uint8_t)kind;
     if (a.state) store_env(e, a.state, a.n_games, g);
-}
-
-// slot of this lane in a shared list: lanes with `want` take consecutive slots starting at the counter's old value
-__device__ __forceinline__ int pool_append(int *counter, bool want, int lane)
-{
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
-    int base = 0;
-    if (m && lane == __ffs(m) - 1) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, m ? __ffs(m) - 1 : 0);
-    return base + __popc(m & ((1u << lane) - 1u));
 }
 
 template <int P, int MODE, int NW>
@@ -307,182 +230,141 @@ __global__ void __launch_bounds__(32 * NW, SPL_POOL_BLOCKS_PER_SM) playout_pool_
     Sm &S = *reinterpret_cast<Sm *>(pool_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 16) S.ctr[threadIdx.x] = 0;
-    if (threadIdx.x < 2) S.n_alive[threadIdx.x] = 0;
-    if (threadIdx.x < 8) S.fam_cnt[threadIdx.x >> 2][threadIdx.x & 3] = 0;
+    if (threadIdx.x < 3) S.n_alive[threadIdx.x] = 0;
     stage_tables(S.T);  // ends with a block barrier
     const Tables &T = S.T;
 
     // the launch's games are split evenly over the blocks; a block starts them as slots of its pool come free
-    const int64_t g_hi = a.n_games * (int64_t)(blockIdx.x + 1) / gridDim.x;
-    int64_t next = a.n_games * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t g_lo = a.n_games * (int64_t)blockIdx.x / gridDim.x;
+    const int n_mine = (int)(a.n_games * (int64_t)(blockIdx.x + 1) / gridDim.x - g_lo);
+    int started = 0;
 
-    for (int round = 0;; round++) {
-        const int b = round & 1;
-        const int nA = S.n_alive[b];
-        const int chunks = (nA + 31) >> 5;
-        const int64_t left = g_hi - next;
-        int n_new = min(NW - chunks, (CAP - nA) >> 5);
-        n_new = (int)min((int64_t)n_new, (left + 31) >> 5);
-        if (chunks == 0 && n_new == 0) break;
-        const bool stepper = warp < chunks;
-        const int p = warp * 32 + lane;
-        const bool valid = stepper && p < nA;
-        const int64_t g_new = next + (int64_t)(warp - chunks) * 32 + lane;
-        const bool loading = !stepper && warp - chunks < n_new && g_new < g_hi;
-
-        Env<P> e;
-        uint32_t gid = 0, t0 = 0, w0 = 0, w1 = 0, w2 = 0;
-        FamilyCounts f;
-        int fam = 4, rank = 0;
-        bool fresh_alive = false;
-        // ------------------------------------------------------------------ phase A (and the loading of new games)
-        if (valid) {
-            pool_load<P, NW>(e, S.st[0], p);
-            gid = S.gid[0][p]; t0 = S.t0[0][p];
-            const uint64_t game = (MODE == POOL_STATES && a.game_ids) ? a.game_ids[gid] : a.first_game + gid;
-            const uint32_t r = philox_rk(a.rk, game, turns_total(e), STREAM_ACTION).x;
-            Ctx c;
-            make_ctx(e, T, c);
-            const int total = count_legal(e, T, c, f);
-            int kf;
-            fam = family_of_k(c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), kf);
-            w0 = (uint32_t)kf | (uint32_t)fam << 13 | c.S << 15 | (uint32_t)c.hold << 20 | (c.bank_yellow ? 1u << 24 : 0u);
-            w1 = c.h1 | c.h2 << 6 | c.h3 << 12 | c.occ << 18;
-            w2 = c.near;
-        } else if (loading) {
-            gid = (uint32_t)g_new;
-            if (MODE == POOL_FRESH) {
-                reset_env(e, a.seed, a.first_game + (uint64_t)g_new, a.rk);
-                fresh_alive = true;
-            } else {
-                load_env(e, a.state, a.n_games, g_new);
-                t0 = turns_total(e);
-                const int kind0 = game_ends(e, a.flags);
-                fresh_alive = kind0 == SPL_END_NONE;
-                if (!fresh_alive) pool_finalize(e, a, S.ctr, g_new, 0, kind0);  // the game was over when it was handed in
+    // Warps 0 .. NW-2 step; the last warp is the KEEPER: it never steps, it carries the (at most 32) live games beyond the
+    // steppers' 32 * (NW - 1) over to the next round untouched and starts new games in its remaining lanes - so the list is
+    // topped up every round and the stepping warps stay full.  Stepping warps that have no group this round (start of the
+    // launch, small launches, the drain at the end) start new games as well, 32 each.
+    constexpr int SCAP = 32 * (NW - 1);
+    for (int round = 0, r3 = 0;; round++, r3 = r3 == 2 ? 0 : r3 + 1) {
+        const int b = round & 1, r3n = r3 == 2 ? 0 : r3 + 1, r3z = r3n == 2 ? 0 : r3n + 1;
+        const int nA = S.n_alive[r3];
+        const int n_step = min(nA, SCAP), chunks = (n_step + 31) >> 5, carried = nA - n_step;
+        // new games this round: the keeper's free lanes first, then 32 per idle stepping warp; never more than fit the list
+        const int room = min(min(CAP - nA, n_mine - started), (32 - carried) + 32 * (NW - 1 - chunks));
+        if (nA == 0 && room == 0) break;
+        if (threadIdx.x == 0) S.n_alive[r3z] = 0;  // last read in the previous round, next appended to in the next one
+        const bool keeper = warp == NW - 1, stepper = warp < chunks;
+        const int p = keeper ? SCAP + lane : warp * 32 + lane;
+        const bool valid = keeper ? lane < carried : (stepper && p < n_step);
+        // fresh-game slot of this lane: keeper lanes carried .. 31 -> 0 .., idle stepping warp j -> (32 - carried) + 32 j + lane
+        const int j_new = keeper ? lane - carried : (32 - carried) + (warp - chunks) * 32 + lane;
+        const bool loading = !valid && !stepper && j_new >= 0 && j_new < room;
+        const int i_new = started + j_new;
+        started += room;
+        // a scheduler (warp id mod 4) that holds one stepping warp fewer than the fullest one would idle at the barrier:
+        // its warps play one move more per round (games are independent, so rounds need not be the same length for all)
+        const int heavy = (chunks + 3) >> 2, mine = (chunks - (warp & 3) + 3) >> 2;
+        const int n_steps = SPL_POOL_STEPS + ((chunks & 3) && mine < heavy ? 1 : 0);
+        if (stepper || keeper || room > 0) {  // warp-uniform: a warp with nothing to do goes straight to the barrier
+            Env<P> e;
+            uint32_t gid = 0, t0 = 0;
+            int kind = SPL_END_NONE, t = 0;
+            bool survive = false;
+            if (valid) {
+                pool_load<P, NW>(e, S.st[b], p);
+                gid = S.gid[b][p]; t0 = S.t0[b][p];
+                survive = true;
+                if (!keeper) {
+                    const uint64_t game = (MODE == POOL_STATES && a.game_ids) ? a.game_ids[gid] : a.first_game + gid;
+                    const DeckSrc src{(MODE != POOL_FRESH && a.decks) ? a.decks + (int64_t)gid * SPL_DECK_BYTES : nullptr, a.seed, game, a.rk};
+                    t = (int)turns_total(e);
+                    const int t_end = (int)t0 + a.max_steps;
+                    if (MODE == POOL_STATES) kind = game_ends(e, a.flags);  // a game that was over when it was handed in
+#pragma unroll 1
+                    for (int s = 0; s < n_steps && kind == SPL_END_NONE; s++) {
+                        Ctx c;
+                        FamilyCounts f;
+                        Choice ch;
+                        const uint32_t r = philox_rk(a.rk, game, (uint32_t)t, STREAM_ACTION).x;
+                        make_ctx(e, T, c);
+                        const int total = count_legal(e, T, c, f);
+                        select_legal(e, T, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
+                        if (__builtin_expect(t < a.trace_len, 0)) a.trace[(int64_t)t * a.n_games + gid] = (int16_t)ch.idx;
+                        apply_action<P, false>(e, ch, src);
+                        t++;
+                        kind = game_ends(e, a.flags);
+                        if (kind == SPL_END_NONE && t >= t_end) kind = SPL_END_TRUNCATED;
+                    }
+                    survive = kind == SPL_END_NONE;
+                }
+            } else if (loading) {
+                gid = (uint32_t)(g_lo + i_new);
+                if (MODE == POOL_FRESH) reset_env(e, a.seed, a.first_game + gid, a.rk);
+                else if (MODE == POOL_LISTS) inject_env(e, a.decks + (int64_t)gid * SPL_DECK_BYTES, a.nobles + (int64_t)gid * 5);
+                else { load_env(e, a.state, a.n_games, (int64_t)gid); t0 = turns_total(e); }
+                survive = true;
             }
-        }
-        if (stepper) {  // slot inside the family (all 32 lanes take part; lanes beyond the list carry fam == 4)
-#pragma unroll
-            for (int F = 0; F < 4; F++) {
-                const int slot = pool_append(&S.fam_cnt[b][F], fam == F, lane);
-                if (fam == F) rank = slot;
+            // survivors, carried and new games -> the next round's list (lanes with `survive` take consecutive slots)
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, survive);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&S.n_alive[r3n], __popc(m));
+                const int q = __shfl_sync(0xFFFFFFFFu, base, leader) + __popc(m & ((1u << lane) - 1u));
+                if (survive) {
+                    pool_store<P, NW>(e, S.st[b ^ 1], q);
+                    S.gid[b ^ 1][q] = gid; S.t0[b ^ 1][q] = t0;
+                }
             }
+            if (valid && !survive) pool_finalize(e, a, S.ctr, (int64_t)gid, t - (int)t0, kind);
         }
-        __syncthreads();  // ---- barrier 1: family totals are final; every read of the live list st[0] is done
-        if (threadIdx.x == 0) {
-            S.n_alive[b] = 0;  // this round's count has been read by everybody; it is the next round's append counter
-#pragma unroll
-            for (int F = 0; F < 4; F++) S.fam_cnt[b ^ 1][F] = 0;
-        }
-        if (valid) {
-            int base = 0;
-#pragma unroll
-            for (int F = 0; F < 3; F++) base += fam > F ? S.fam_cnt[b][F] : 0;
-            const int q = base + rank;
-            pool_store<P, NW>(e, S.st[1], q);
-            S.gid[1][q] = gid; S.t0[1][q] = t0;
-            S.pw[0][q] = w0; S.pw[1][q] = w1;
-            if (fam == FAM_COLLECT) {
-#pragma unroll
-                for (int i = 0; i < 9; i++) S.pw[2 + i][q] = f.grp[i];
-            } else if (fam == FAM_BUY) {
-                S.pw[2][q] = w2;
-#pragma unroll
-                for (int i = 0; i < 4; i++) S.pw[3 + i][q] = f.buy[i];
-            }
-        }
-        __syncthreads();  // ---- barrier 2: the sorted list is complete
-        // ------------------------------------------------------------------ phase B
-        bool survive = fresh_alive;
-        int kind = SPL_END_NONE, t = 0;
-        if (valid) {
-            pool_load<P, NW>(e, S.st[1], p);
-            gid = S.gid[1][p]; t0 = S.t0[1][p];
-            w0 = S.pw[0][p]; w1 = S.pw[1][p];
-            fam = (int)(w0 >> 13 & 3u);
-            const int kf = (int)(w0 & 0x1FFFu);
-            const uint64_t game = (MODE == POOL_STATES && a.game_ids) ? a.game_ids[gid] : a.first_game + gid;
-            const DeckSrc src{(MODE == POOL_STATES && a.decks) ? a.decks + (int64_t)gid * SPL_DECK_BYTES : nullptr, a.seed, game, a.rk};
-            Ctx c;
-            const int seat = seat_of(e.meta);
-            c.gems = e.pg[0]; c.cards = e.pc[0]; c.resv = e.pr[0];
-#pragma unroll
-            for (int q = 1; q < P; q++)
-                if (seat == q) { c.gems = e.pg[q]; c.cards = e.pc[q]; c.resv = e.pr[q]; }
-            c.bank = e.bank;
-            c.S = w0 >> 15 & 31u; c.nS = c.S ? __popc(c.S) : 1;
-            c.hold = (int)(w0 >> 20 & 15u); c.bank_yellow = w0 >> 24 & 1u;
-            c.h1 = w1 & 63u; c.h2 = w1 >> 6 & 63u; c.h3 = w1 >> 12 & 63u; c.occ = w1 >> 18;
-            c.yellow = (int)field(c.gems, YSH);
-            c.near = 0;
-            Choice ch;
-            if (fam == FAM_COLLECT) {
-#pragma unroll
-                for (int i = 0; i < 9; i++) f.grp[i] = S.pw[2 + i][p];
-                select_family(e, T, c, f, FAM_COLLECT, kf, ch);
-            } else if (fam == FAM_RESERVE) {
-                select_family(e, T, c, f, FAM_RESERVE, kf, ch);
-            } else if (fam == FAM_BUY) {
-                c.near = S.pw[2][p];
-#pragma unroll
-                for (int i = 0; i < 4; i++) f.buy[i] = S.pw[3 + i][p];
-                select_family(e, T, c, f, FAM_BUY, kf, ch);
-            } else {
-                select_family(e, T, c, f, FAM_PASS, kf, ch);
-            }
-            t = (int)turns_total(e);
-            if (__builtin_expect(t < a.trace_len, 0)) a.trace[(int64_t)t * a.n_games + gid] = (int16_t)ch.idx;
-            apply_action<P, false>(e, ch, src);
-            t++;
-            kind = game_ends(e, a.flags);
-            if (kind == SPL_END_NONE && t - (int)t0 >= a.max_steps) kind = SPL_END_TRUNCATED;
-            survive = kind == SPL_END_NONE;
-        }
-        if (stepper || n_new) {  // warp-uniform: the stepping warps and (when games are being started) the others
-            const int q = pool_append(&S.n_alive[b ^ 1], survive, lane);
-            if (survive) {
-                pool_store<P, NW>(e, S.st[0], q);
-                S.gid[0][q] = gid; S.t0[0][q] = t0;
-            }
-        }
-        if (valid && !survive) pool_finalize(e, a, S.ctr, (int64_t)gid, t - (int)t0, kind);
-        next = min(g_hi, next + (int64_t)n_new * 32);
-        __syncthreads();  // ---- barrier 3: the next round's live list is complete
+        __syncthreads();  // the next round's list is complete; this round's list may be overwritten
     }
-    if (a.counters && threadIdx.x < 16 && S.ctr[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], S.ctr[threadIdx.x]);
+    if (a.counters && threadIdx.x < 16 && S.ctr[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], (unsigned long long)S.ctr[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------- step
+// Persistent: the grid is (SMs x resident blocks), every block stages the tables ONCE and strides over the envs; the first
+// env's action and state loads are issued before the table copy and its barrier.
 template <int P>
-__global__ void __launch_bounds__(BLOCK) step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
-                                                     const uint64_t *game_ids, const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal,
-                                                     int64_t N, uint32_t flags)
+__global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+                                                      const uint64_t *game_ids, const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal,
+                                                      int64_t N, uint32_t flags)
 {
-    __shared__ Tables sT;
-    stage_tables(sT);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int a = action[i];
+    __shared__ __align__(16) Tables sT;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Env<P> e;
-    load_env(e, state, N, i);
-    int rew = 0, bad = 0;
-    if (a >= 0) {
-        Ctx c;
-        Choice ch;
-        make_ctx(e, sT, c);
-        if (decode_and_check(e, sT, c, a, ch)) {
-            const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
-            rew = apply_action(e, ch, src);
-        } else {
-            bad = 1;
-            e.meta |= META_ILLEGAL;
-        }
-        store_env(e, state, N, i);
+    int a = -1;
+    if (i < N) {
+        a = action[i];
+        load_env(e, state, N, i);
     }
-    if (reward) reward[i] = (int8_t)rew;
-    if (illegal) illegal[i] = (uint8_t)bad;
-    if (done) done[i] = (uint8_t)game_ends(e, flags);
+    stage_tables_nosync(sT);
+    __syncthreads();
+    while (i < N) {
+        int rew = 0, bad = 0;
+        if (a >= 0) {
+            Ctx c;
+            Choice ch;
+            make_ctx(e, sT, c);
+            if (decode_and_check(e, sT, c, a, ch)) {
+                const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
+                rew = apply_action(e, ch, src);
+            } else {
+                bad = 1;
+                e.meta |= META_ILLEGAL;
+            }
+            store_env(e, state, N, i);
+        }
+        if (reward) reward[i] = (int8_t)rew;
+        if (illegal) illegal[i] = (uint8_t)bad;
+        if (done) done[i] = (uint8_t)game_ends(e, flags);
+        i += stride;
+        if (i < N) {
+            a = action[i];
+            load_env(e, state, N, i);
+        }
+    }
 }
 
 template <int P>
@@ -779,45 +661,58 @@ __global__ void __launch_bounds__(TILE_TB_MAX) observe_kernel(const uint4 *state
 // three was slower (0.214 ms against 0.16 ms per 262,144 envs) because the shared-memory tile of the row kernels caps
 // residency at 14 warps per SM, and this latency-bound part then runs at that occupancy too.
 template <int P>
-__global__ void __launch_bounds__(BLOCK) env_move_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
-                                                         const uint64_t *game_ids, const int8_t *learner, const int16_t *action,
-                                                         int8_t *reward, uint8_t *terminated, uint8_t *illegal, int64_t N, uint32_t flags)
+__global__ void __launch_bounds__(ENV_TB) env_move_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+                                                          const uint64_t *game_ids, const int8_t *learner, const int16_t *action,
+                                                          int8_t *reward, uint8_t *terminated, uint8_t *illegal, int64_t N, uint32_t flags)
 {
-    __shared__ Tables sT;
-    stage_tables(sT);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    Env<P> e;
-    load_env(e, state, N, i);
+    __shared__ __align__(16) Tables sT;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool self_play = flags & SPL_F_SELF_PLAY;
-    const int me = self_play ? seat_of(e.meta) : (int)learner[i];
-    const int a = action[i];
-    const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
-    int rew = 0, bad = 0;
-    bool go = true;
-    if (a >= 0) {
-        Ctx c;
-        Choice ch;
-        make_ctx(e, sT, c);
-        if (seat_of(e.meta) == me && game_ends(e, flags) == SPL_END_NONE && decode_and_check(e, sT, c, a, ch))
-            rew = apply_action(e, ch, src);
-        else { bad = 1; go = false; e.meta |= META_ILLEGAL; }
+    Env<P> e;
+    int a = -1, me = 0;
+    if (i < N) {  // the first env's loads go out before the table copy and its barrier
+        a = action[i];
+        me = self_play ? 0 : (int)learner[i];
+        load_env(e, state, N, i);
     }
-    for (int guard = 0; go && !self_play && guard < 4; guard++) {
-        if (seat_of(e.meta) == me || game_ends(e, flags) != SPL_END_NONE) break;
-        Ctx c;
-        FamilyCounts f;
-        Choice ch;
-        const uint32_t r = philox(seed, src.game, turns_total(e), STREAM_ACTION).x;
-        make_ctx(e, sT, c);
-        const int total = count_legal(e, sT, c, f);
-        select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
-        apply_action(e, ch, src);
+    stage_tables_nosync(sT);
+    __syncthreads();
+    while (i < N) {
+        if (self_play) me = seat_of(e.meta);
+        const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
+        int rew = 0, bad = 0;
+        bool go = true;
+        if (a >= 0) {
+            Ctx c;
+            Choice ch;
+            make_ctx(e, sT, c);
+            if (seat_of(e.meta) == me && game_ends(e, flags) == SPL_END_NONE && decode_and_check(e, sT, c, a, ch))
+                rew = apply_action(e, ch, src);
+            else { bad = 1; go = false; e.meta |= META_ILLEGAL; }
+        }
+        for (int guard = 0; go && !self_play && guard < 4; guard++) {
+            if (seat_of(e.meta) == me || game_ends(e, flags) != SPL_END_NONE) break;
+            Ctx c;
+            FamilyCounts f;
+            Choice ch;
+            const uint32_t r = philox(seed, src.game, turns_total(e), STREAM_ACTION).x;
+            make_ctx(e, sT, c);
+            const int total = count_legal(e, sT, c, f);
+            select_legal(e, sT, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
+            apply_action(e, ch, src);
+        }
+        store_env(e, state, N, i);
+        if (reward) reward[i] = (int8_t)rew;
+        if (illegal) illegal[i] = (uint8_t)bad;
+        if (terminated) terminated[i] = (uint8_t)game_ends(e, flags);
+        i += stride;
+        if (i < N) {
+            a = action[i];
+            me = self_play ? 0 : (int)learner[i];
+            load_env(e, state, N, i);
+        }
     }
-    store_env(e, state, N, i);
-    if (reward) reward[i] = (int8_t)rew;
-    if (illegal) illegal[i] = (uint8_t)bad;
-    if (terminated) terminated[i] = (uint8_t)game_ends(e, flags);
 }
 
 // ---------------------------------------------------------------------------------------------- masked action sampling
@@ -959,16 +854,26 @@ static int check_device()
     return SPL_OK;
 }
 static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
-static int sm_count()
+constexpr int SPL_MAX_DEVICES = 64;
+static int sm_count()  // of the CURRENT device (cached per device: a process may drive several GPUs)
 {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static int sms[SPL_MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= SPL_MAX_DEVICES) return 148;
+    if (!sms[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
     }
-    return sms;
+    return sms[dev];
+}
+
+// persistent thread-per-env kernels: one block per ENV_TB envs, capped at what is resident at once (the blocks stride)
+static unsigned persistent_grid(int64_t n, int blocks_per_sm)
+{
+    const int64_t want = (n + ENV_TB - 1) / ENV_TB, cap = (int64_t)sm_count() * blocks_per_sm;
+    return (unsigned)(want < cap ? want : cap);
 }
 
 // tile kernels: block size (a multiple of 32, overridable for experiments), dynamic shared memory above 48 KB, residency
@@ -1004,14 +909,13 @@ static int launch_pool(const PlayoutArgs &a, cudaStream_t stream)
     constexpr int NW = SPL_POOL_WARPS;
     using Sm = PoolSmem<P, NW>;
     auto kernel = playout_pool_kernel<P, MODE, NW>;
-    static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
+    static bool configured[SPL_MAX_DEVICES] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
     int dev = 0;
     CK(cudaGetDevice(&dev));
-    if (dev < 16 && !configured[dev]) {
+    if (dev < 0 || dev >= SPL_MAX_DEVICES) return SPL_E_BADARG;
+    if (!configured[dev]) {
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sm)));
         configured[dev] = true;
-    } else if (dev >= 16) {
-        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sm)));
     }
     const int64_t cap = (int64_t)sm_count() * SPL_POOL_BLOCKS_PER_SM, want = (a.n_games + 31) / 32;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
@@ -1104,7 +1008,7 @@ int spl_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_ga
     if (!state || !action || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    DISPATCH_P(P, step_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
+    DISPATCH_P(P, step_kernel<PP><<<persistent_grid(N, STEP_BLOCKS_PER_SM), ENV_TB, 0, (cudaStream_t)stream>>>(
                       (uint4 *)state, decks, seed, first_game, game_ids, action, reward, done, illegal, N, flags));
     CK(cudaGetLastError());
     return SPL_OK;
@@ -1206,7 +1110,7 @@ int spl_observe(const void *state, const int8_t *seat, float *obs, int64_t N, in
     return launch_observe(state, seat, obs, N, P, (cudaStream_t)stream);
 }
 
-static int launch_playout(bool fresh, const PlayoutArgs &args, int P, cudaStream_t stream)
+static int launch_playout(int mode, const PlayoutArgs &args, int P, cudaStream_t stream)
 {
     PlayoutArgs a = args;
     philox_round_keys(a.seed, a.rk);
@@ -1214,26 +1118,9 @@ static int launch_playout(bool fresh, const PlayoutArgs &args, int P, cudaStream
     if (!a.trace) a.trace_len = 0;  // the kernel tests trace_len only
     if (a.trace && a.trace_len > 0)
         CK(cudaMemsetAsync(a.trace, 0xFF, (size_t)a.trace_len * (size_t)a.n_games * sizeof(int16_t), stream));
-    static int impl = -1;
-    if (impl < 0) {  // SPL_PLAYOUT_IMPL=thread: the one-game-per-thread kernel (A/B only)
-        const char *s = getenv("SPL_PLAYOUT_IMPL");
-        impl = (s && !strcmp(s, "thread")) ? 1 : 0;
-    }
-    if (impl == 0) {
-        if (fresh) { DISPATCH_P(P, if (int rc = launch_pool<PP, POOL_FRESH>(a, stream)) return rc); }
-        else { DISPATCH_P(P, if (int rc = launch_pool<PP, POOL_STATES>(a, stream)) return rc); }
-        CK(cudaGetLastError());
-        return SPL_OK;
-    }
-    static int blk = 0;
-    if (!blk) {  // SPL_PLAYOUT_BLOCK: threads per block (32, 64, 96 or 128) - a tuning knob, see profiles/r1_playout_ncu.md
-        const char *s = getenv("SPL_PLAYOUT_BLOCK");
-        blk = s ? atoi(s) : PLAYOUT_BLOCK;
-        if (blk != 32 && blk != 64 && blk != 96 && blk != 128) blk = PLAYOUT_BLOCK;
-    }
-    const unsigned grid = (unsigned)((a.n_games + blk - 1) / blk);
-    if (fresh) { DISPATCH_P(P, playout_kernel<PP, true><<<grid, blk, 0, stream>>>(a)); }
-    else { DISPATCH_P(P, playout_kernel<PP, false><<<grid, blk, 0, stream>>>(a)); }
+    if (mode == POOL_FRESH) { DISPATCH_P(P, if (int rc = launch_pool<PP, POOL_FRESH>(a, stream)) return rc); }
+    else if (mode == POOL_STATES) { DISPATCH_P(P, if (int rc = launch_pool<PP, POOL_STATES>(a, stream)) return rc); }
+    else { DISPATCH_P(P, if (int rc = launch_pool<PP, POOL_LISTS>(a, stream)) return rc); }
     CK(cudaGetLastError());
     return SPL_OK;
 }
@@ -1245,9 +1132,9 @@ int spl_playout(uint64_t seed, uint64_t first_game, int64_t num_games, int P, ui
     if (num_games < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (num_games == 0) return SPL_OK;
-    PlayoutArgs a{(uint4 *)final_state, nullptr, seed, first_game, nullptr, num_games, flags, max_steps, score2, steps, end_kind,
+    PlayoutArgs a{(uint4 *)final_state, nullptr, nullptr, seed, first_game, nullptr, num_games, flags, max_steps, score2, steps, end_kind,
                   (unsigned long long *)counters, trace, trace_len};
-    return launch_playout(true, a, P, (cudaStream_t)stream);
+    return launch_playout(POOL_FRESH, a, P, (cudaStream_t)stream);
 }
 
 int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids, int64_t N,
@@ -1257,9 +1144,9 @@ int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t 
     if (!state || N < 0) return SPL_E_BADARG;
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
-    PlayoutArgs a{(uint4 *)state, decks, seed, first_game, game_ids, N, flags, max_steps, score2, steps, end_kind,
+    PlayoutArgs a{(uint4 *)state, decks, nullptr, seed, first_game, game_ids, N, flags, max_steps, score2, steps, end_kind,
                   (unsigned long long *)counters, trace, trace_len};
-    return launch_playout(false, a, P, (cudaStream_t)stream);
+    return launch_playout(POOL_STATES, a, P, (cudaStream_t)stream);
 }
 
 int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
@@ -1270,7 +1157,7 @@ int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t firs
     if (int rc = check_device()) return rc;
     if (N == 0) return SPL_OK;
     const int8_t *seat = (flags & SPL_F_SELF_PLAY) ? nullptr : learner;  // self-play: whoever moves next
-    DISPATCH_P(P, env_move_kernel<PP><<<grid_for(N, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
+    DISPATCH_P(P, env_move_kernel<PP><<<persistent_grid(N, ENV_MOVE_BLOCKS_PER_SM), ENV_TB, 0, (cudaStream_t)stream>>>(
                       (uint4 *)state, decks, seed, first_game, game_ids, learner, action, reward, terminated, illegal, N, flags));
     CK(cudaGetLastError());
     if (obs)
@@ -1280,7 +1167,7 @@ int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t firs
     return SPL_OK;
 }
 
-// ---- host-buffer path: library-owned, grow-only device staging
+// ---- host-buffer path: library-owned, grow-only device staging, one set per (device, slot)
 namespace {
 struct Staging {
     void *p = nullptr;
@@ -1298,51 +1185,33 @@ struct Staging {
 std::mutex g_stage_mu;
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// One of the two independent pipelines of the host-buffer path: its own staging memory, chunk streams and events, so
-// that two calls in flight (spl_playout_host_async on alternating slots) share nothing but the GPU.
-constexpr int HOST_SLOTS = 2, MAX_CHUNKS = 8, HOST_CHUNKS_DEFAULT = 4;
+// One pipeline of the host-buffer path: its own staging memory and completion event, so that two calls in flight
+// (spl_playout_host_async on alternating slots) share nothing but the GPU.  Slots belong to a DEVICE: a process that drives
+// several GPUs gets separate staging memory and events on each (the current device at the time of the call).
+constexpr int HOST_SLOTS = 2;
 struct HostSlot {
     Staging stage;
-    cudaStream_t side[MAX_CHUNKS] = {};
-    cudaEvent_t ev_start = nullptr, ev_done[MAX_CHUNKS] = {}, ev_call_done = nullptr;
+    cudaEvent_t ev_call_done = nullptr;
     bool used = false;
-    int init()
-    {
-        if (ev_start) return SPL_OK;
-        CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_call_done, cudaEventDisableTiming));
-        for (int c = 0; c < MAX_CHUNKS; c++) {
-            CK(cudaStreamCreateWithFlags(&side[c], cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
-        }
-        return SPL_OK;
-    }
 };
-HostSlot g_slots[HOST_SLOTS];
+HostSlot g_slots[SPL_MAX_DEVICES][HOST_SLOTS];
 
-// Everything of a host-buffer playout up to (not including) the wait for its completion: on return the copies and
-// kernels are queued, `ctr_out` (host, 16 x int64) and the output arrays are written when `stream` reaches the end of
-// the queued work.  Caller holds g_stage_mu.
-int playout_host_enqueue(HostSlot &S, const uint8_t *deck_lists, const uint8_t *nobles, uint64_t seed, uint64_t first_game, int64_t N,
+// Everything of a host-buffer playout up to (not including) the wait for its completion, all on the caller's stream:
+//   2 H2D copies (deck orders, nobles) -> ONE kernel that builds every game from its deck order and plays it to the end
+//   (playout_pool_kernel<P, POOL_LISTS>: no separate inject pass, no state array in HBM) -> 4 D2H copies.
+// 10 CUDA API calls per batch (round 1 issued ~35: four chunks on side streams, each with its own inject + playout + events).
+// On return the work is queued; `ctr_out` (host, 16 x int64) and the output arrays are written when `stream` gets there.
+// Caller holds g_stage_mu.
+int playout_host_enqueue(int slot, const uint8_t *deck_lists, const uint8_t *nobles, uint64_t seed, uint64_t first_game, int64_t N,
                          int P, uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind, int64_t *ctr_out,
                          cudaStream_t stream)
 {
-    if (int rc = S.init()) return rc;
-    // The batch is cut into chunks that travel on separate internal streams: the H2D copy of chunk k+1 and the D2H copy
-    // of chunk k-1 overlap the kernels of chunk k (and the chunk kernels, latency-bound at this size, overlap each other).
-    static int want_chunks = 0;
-    if (!want_chunks) {  // SPL_HOST_CHUNKS: 1..8, a tuning knob (profiles/r1q_playout.md)
-        const char *s = getenv("SPL_HOST_CHUNKS");
-        want_chunks = s ? atoi(s) : HOST_CHUNKS_DEFAULT;
-        if (want_chunks < 1 || want_chunks > MAX_CHUNKS) want_chunks = HOST_CHUNKS_DEFAULT;
-    }
-    const int n_chunks = N >= 16384 ? want_chunks : 1;
-    // equal chunks: sizes shrinking towards the end (so that the last kernel's longest game is shorter in expectation)
-    // measured 1.5 % slower (profiles/r1q_playout.md)
-    const int64_t per = ((N + n_chunks - 1) / n_chunks + 127) / 128 * 128;
-    const size_t W = (size_t)(8 + 4 * P) * 4;
-    const size_t o_state = 0, o_decks = o_state + align256((size_t)N * W) + 256 * MAX_CHUNKS,
-                 o_nobles = o_decks + align256((size_t)N * SPL_DECK_BYTES), o_score = o_nobles + align256((size_t)N * 5),
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= SPL_MAX_DEVICES) return SPL_E_BADARG;
+    HostSlot &S = g_slots[dev][slot];
+    if (!S.ev_call_done) CK(cudaEventCreateWithFlags(&S.ev_call_done, cudaEventDisableTiming));
+    const size_t o_decks = 0, o_nobles = o_decks + align256((size_t)N * SPL_DECK_BYTES), o_score = o_nobles + align256((size_t)N * 5),
                  o_steps = o_score + align256((size_t)N * P), o_kind = o_steps + align256((size_t)N * 2),
                  o_ctr = o_kind + align256((size_t)N), total = o_ctr + 256;
     if (total > S.stage.cap && S.used) CK(cudaEventSynchronize(S.ev_call_done));  // growing frees the old buffer: let its last user finish
@@ -1352,28 +1221,14 @@ int playout_host_enqueue(HostSlot &S, const uint8_t *deck_lists, const uint8_t *
     // slots as documented never blocks here; one that does not is serialised instead of corrupted)
     if (S.used) CK(cudaStreamWaitEvent(stream, S.ev_call_done, 0));
     CK(cudaMemsetAsync(b + o_ctr, 0, 128, stream));
-    CK(cudaEventRecord(S.ev_start, stream));
-    size_t state_off = o_state;
-    for (int c = 0; c < n_chunks; c++) {
-        const int64_t lo = (int64_t)c * per, n = (lo + per <= N ? per : N - lo);
-        if (n <= 0) break;
-        cudaStream_t s = S.side[c];
-        CK(cudaStreamWaitEvent(s, S.ev_start, 0));
-        char *st = b + state_off;  // each chunk is its own chunk-major state batch of n envs
-        state_off += align256((size_t)n * W);
-        CK(cudaMemcpyAsync(b + o_decks + lo * SPL_DECK_BYTES, deck_lists + lo * SPL_DECK_BYTES, (size_t)n * SPL_DECK_BYTES, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(b + o_nobles + lo * 5, nobles + lo * 5, (size_t)n * 5, cudaMemcpyHostToDevice, s));
-        if (int rc = spl_inject(st, (const uint8_t *)(b + o_decks + lo * SPL_DECK_BYTES), (const uint8_t *)(b + o_nobles + lo * 5), n, P, s)) return rc;
-        if (int rc = spl_playout_from(st, (const uint8_t *)(b + o_decks + lo * SPL_DECK_BYTES), seed, first_game + (uint64_t)lo, nullptr, n, P,
-                                      flags, max_steps, (int8_t *)(b + o_score) + lo * P, (int16_t *)(b + o_steps) + lo,
-                                      (uint8_t *)(b + o_kind) + lo, (int64_t *)(b + o_ctr), nullptr, 0, s))
-            return rc;
-        if (score2) CK(cudaMemcpyAsync(score2 + lo * P, b + o_score + lo * P, (size_t)n * P, cudaMemcpyDeviceToHost, s));
-        if (steps) CK(cudaMemcpyAsync(steps + lo, b + o_steps + lo * 2, (size_t)n * 2, cudaMemcpyDeviceToHost, s));
-        if (end_kind) CK(cudaMemcpyAsync(end_kind + lo, b + o_kind + lo, (size_t)n, cudaMemcpyDeviceToHost, s));
-        CK(cudaEventRecord(S.ev_done[c], s));
-        CK(cudaStreamWaitEvent(stream, S.ev_done[c], 0));
-    }
+    CK(cudaMemcpyAsync(b + o_decks, deck_lists, (size_t)N * SPL_DECK_BYTES, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(b + o_nobles, nobles, (size_t)N * 5, cudaMemcpyHostToDevice, stream));
+    PlayoutArgs a{nullptr, (const uint8_t *)(b + o_decks), (const uint8_t *)(b + o_nobles), seed, first_game, nullptr, N, flags, max_steps,
+                  (int8_t *)(b + o_score), (int16_t *)(b + o_steps), (uint8_t *)(b + o_kind), (unsigned long long *)(b + o_ctr), nullptr, 0};
+    if (int rc = launch_playout(POOL_LISTS, a, P, stream)) return rc;
+    if (score2) CK(cudaMemcpyAsync(score2, b + o_score, (size_t)N * P, cudaMemcpyDeviceToHost, stream));
+    if (steps) CK(cudaMemcpyAsync(steps, b + o_steps, (size_t)N * 2, cudaMemcpyDeviceToHost, stream));
+    if (end_kind) CK(cudaMemcpyAsync(end_kind, b + o_kind, (size_t)N, cudaMemcpyDeviceToHost, stream));
     if (ctr_out) CK(cudaMemcpyAsync(ctr_out, b + o_ctr, 128, cudaMemcpyDeviceToHost, stream));
     CK(cudaEventRecord(S.ev_call_done, stream));
     S.used = true;
@@ -1391,7 +1246,7 @@ int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     std::lock_guard<std::mutex> lock(g_stage_mu);
     int64_t ctr[16];
-    if (int rc = playout_host_enqueue(g_slots[0], deck_lists, nobles, seed, first_game, N, P, flags, max_steps, score2, steps, end_kind,
+    if (int rc = playout_host_enqueue(0, deck_lists, nobles, seed, first_game, N, P, flags, max_steps, score2, steps, end_kind,
                                       ctr, stream))
         return rc;
     CK(cudaStreamSynchronize(stream));
@@ -1411,7 +1266,7 @@ int spl_playout_host_async(const uint8_t *deck_lists, const uint8_t *nobles, uin
         return SPL_OK;
     }
     std::lock_guard<std::mutex> lock(g_stage_mu);
-    return playout_host_enqueue(g_slots[slot], deck_lists, nobles, seed, first_game, N, P, flags, max_steps, score2, steps, end_kind,
+    return playout_host_enqueue(slot, deck_lists, nobles, seed, first_game, N, P, flags, max_steps, score2, steps, end_kind,
                                 counters, (cudaStream_t)stream_);
 }
 

@@ -290,9 +290,8 @@ def test_host_buffer_abi_call(pkg, oracle):
     assert np.array_equal(score2, sc) and np.array_equal(steps.astype(np.int32), st) and np.array_equal(ctr, c)
 
 
-def test_host_buffer_abi_call_in_chunks(pkg, oracle):
-    """The chunked form of spl_playout_host (>= 16,384 games: copies and kernels of several chunks overlap on internal
-    streams), with a batch size that leaves a ragged last chunk and a ragged last block."""
+def test_host_buffer_abi_call_with_a_ragged_batch(pkg, oracle):
+    """spl_playout_host with a batch size that is no multiple of the warp or pool size, and a non-zero first game id."""
     import ctypes as C
 
     N, P, seed, first = 20_011, 2, 77, 5_000
@@ -340,41 +339,47 @@ def test_async_host_buffer_calls_pipeline_on_two_slots(pkg, oracle):
                                       2, None) == pkg._native.SPL_E_BADARG  # only slots 0 and 1 exist
 
 
-@pytest.mark.parametrize("knob", [{"SPL_PLAYOUT_BLOCK": "32"}, {"SPL_PLAYOUT_BLOCK": "96"}, {"SPL_HOST_CHUNKS": "3"}])
-def test_tuning_knobs_do_not_change_results(pkg, knob):
-    """SPL_PLAYOUT_BLOCK (threads per block of the playout kernel; also the pitch of the shared-memory deck lists) and
-    SPL_HOST_CHUNKS are read once per process, so the other setting runs in a child process; every per-game output and
-    the final states must be identical."""
-    import subprocess
-    import sys
-    import tempfile
+def test_results_do_not_depend_on_the_launch_geometry(pkg, oracle):
+    """A game's trajectory is a function of (seed, game id) only: the same 5,000 three-player games played in one launch,
+    and cut into launches of very different sizes (so that they land in other pools, other warps and other rounds of the
+    block-pool playout kernel), give identical per-game outputs, traces and final states."""
+    G, P, seed, first = 5000, 3, 5, 123
+    whole = pkg.playout_games(G, P, seed=seed, first_game=first, trace_len=64, want_final_state=True)
+    cuts = [0, 1, 33, 700, 2748, 2749, 4999, 5000]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        part = pkg.playout_games(hi - lo, P, seed=seed, first_game=first + lo, trace_len=64, want_final_state=True)
+        for key in ("score2", "steps", "end_kind"):
+            assert torch.equal(part[key], whole[key][lo:hi]), (key, lo, hi)
+        assert torch.equal(part["trace"], whole["trace"][:, lo:hi]), (lo, hi)
+        assert torch.equal(part["final_state"], whole["final_state"][:, lo:hi]), (lo, hi)
+    assert int(whole["counters"][0]) == G
 
-    code = (
-        "import sys, numpy as np, torch, ctypes as C\n"
-        "sys.path.insert(0, sys.argv[1])\n"
-        "import splendor_ai_b200 as pkg\n"
-        "out = pkg.playout_games(5000, 3, seed=5, first_game=123, trace_len=64, want_final_state=True)\n"
-        "N, P = 17000, 2\n"
-        "eng = pkg.BatchedSplendor(N, P, seed=6, first_game=9)\n"
-        "l, n = eng.reset(want_lists=True)\n"
-        "l, n = l.cpu().numpy(), n.cpu().numpy()\n"
-        "sc, st, kd, ctr = np.zeros((N, P), np.int8), np.zeros(N, np.int16), np.zeros(N, np.uint8), np.zeros(16, np.int64)\n"
-        "p = lambda a: a.ctypes.data_as(C.c_void_p)\n"
-        "assert pkg._native.lib().spl_playout_host(p(l), p(n), 6, 9, N, P, 0, 1000, p(sc), p(st), p(kd), p(ctr), None) == 0\n"
-        "np.savez(sys.argv[2], host_score=sc, host_steps=st, host_kind=kd, host_ctr=ctr, "
-        "**{k: out[k].cpu().numpy() for k in ('score2', 'steps', 'end_kind', 'counters', 'trace', 'final_state')})\n"
-    )
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    results = []
-    with tempfile.TemporaryDirectory() as tmp:
-        for i, extra in enumerate(({}, knob)):
-            env = {k: v for k, v in os.environ.items() if k not in ("SPL_PLAYOUT_BLOCK", "SPL_HOST_CHUNKS")}
-            env.update(extra)
-            path = os.path.join(tmp, f"r{i}.npz")
-            subprocess.run([sys.executable, "-c", code, root, path], check=True, env=env, timeout=600)
-            results.append(dict(np.load(path)))
-    for key in results[0]:
-        assert np.array_equal(results[0][key], results[1][key]), (knob, key)
+
+def test_two_devices_from_one_process(pkg, oracle):
+    """The library keeps its staging memory, events and SM count PER DEVICE: one process drives two GPUs through the
+    host-buffer calls and the device-pointer calls alternately (skipped on a one-GPU box)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    N, P, seed = 6000, 2, 12
+    lib = pkg._native.lib()
+    want = oracle.playout_many(seed, 0, N, P, False, 1000, nthreads=os.cpu_count() or 1)
+    lists = np.stack([oracle.synth_game(seed, g, P)[0] for g in range(N)])
+    nobles = np.full((N, 5), 255, np.uint8)
+    for g in range(N):
+        nobles[g, :P + 1] = oracle.synth_game(seed, g, P)[1]
+    import ctypes as C
+
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for rep in range(2):
+        for d in (0, 1):
+            with torch.cuda.device(d):
+                score2, steps, kind, ctr = np.zeros((N, P), np.int8), np.zeros(N, np.int16), np.zeros(N, np.uint8), np.zeros(16, np.int64)
+                assert lib.spl_playout_host(p(lists), p(nobles), seed, 0, N, P, 0, 1000, p(score2), p(steps), p(kind), p(ctr), None) == 0
+                assert np.array_equal(score2, want[0]) and np.array_equal(steps.astype(np.int32), want[1]) and np.array_equal(ctr, want[2]), (rep, d)
+                out = pkg.playout_games(N, P, seed=seed, device=f"cuda:{d}")
+                assert np.array_equal(out["score2"].cpu().numpy(), want[0]), (rep, d)
+                eng = pkg.BatchedSplendor(256, P, seed=seed, device=f"cuda:{d}")
+                assert eng.legal_mask().device.index == d and eng.observe().device.index == d
 
 
 @pytest.mark.parametrize("P", [2, 3, 4])

@@ -1,5 +1,5 @@
 """Time spl_playout_host (host deck orders in, host results out) for one batch size; prints one JSON line.
-Usage: [SPL_HOST_CHUNKS=2] python tools/perf_e2e.py [--games 65536] [--players 2] [--reps 50]"""
+Usage: python tools/perf_e2e.py [--games 65536] [--players 2] [--reps 50]"""
 import argparse
 import ctypes as C
 import json
@@ -50,5 +50,5 @@ for s in range(a.reps):
     call(s)
 torch.cuda.synchronize(dev)
 dt = time.perf_counter() - t0
-print(json.dumps({"chunks": os.environ.get("SPL_HOST_CHUNKS", "default"), "players": P, "games": G, "ms_per_call": dt / a.reps * 1e3,
+print(json.dumps({"players": P, "games": G, "ms_per_call": dt / a.reps * 1e3,
                   "env_steps_per_s": int(h_ctr[1]) / dt}))

@@ -1,5 +1,5 @@
 """Time spl_playout (fused random playouts) for a few batch sizes; prints one JSON line per configuration.
-Usage: [SPL_PLAYOUT_BLOCK=64] python tools/perf_playout.py [--games 65536 1048576] [--players 2] [--reps 20]"""
+Usage: [SPL_LIB=csrc/variants/x.so] python tools/perf_playout.py [--games 65536 1048576] [--players 2] [--reps 20]"""
 import argparse
 import json
 import os
@@ -32,5 +32,5 @@ for P in a.players:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         steps = int(ctr[1].item())
-        print(json.dumps({"block": os.environ.get("SPL_PLAYOUT_BLOCK", "128"), "players": P, "games": G, "ms_per_launch": ms / a.reps,
+        print(json.dumps({"lib": os.path.basename(os.environ.get("SPL_LIB", "default")), "players": P, "games": G, "ms_per_launch": ms / a.reps,
                           "env_steps_per_s": steps / (ms * 1e-3), "frac_of_hbm_roofline": steps / (ms * 1e-3) * (160 if P == 2 else 224) / 6533.8e9}))
