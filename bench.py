@@ -8,6 +8,10 @@ Workload = BASELINE.json configs[1]: 2-player batched random playouts, 65,536 ga
 to its end inside one fused kernel (spl_playout).  One env-step = one GameRule.update including the legal-action
 computation that precedes it.  Weak scaling: every rank plays its own 65,536-game slice per step (global game ids),
 no data-path collective; one NCCL all-reduce of the int64[16] counter block at the end.
+
+Besides `value` the line carries `sweep`: BASELINE.json configs[4], the 2^24-game two-player sweep split over the N ranks
+by global game id (strong scaling), wall-clock timed from the first launch to the COMPLETED all-reduce of the counter
+block, with the counters compared to the committed single-GPU result (bit-for-bit: they do not depend on N).
 """
 import argparse
 import ctypes as C
@@ -64,37 +68,102 @@ def cpu_port_throughput(P, seconds, batch=2048, first_game=0):
     return steps / dt, cores, games, steps, dt
 
 
+def _python_engine_worker(args):
+    """One process: the UNMODIFIED reference loop (gameEnds -> getLegalActions -> RandomAgent.SelectAction -> update) for
+    `seconds` of wall time.  Runs only if the reference package is importable (baseline/_ref or /root/reference/src)."""
+    path, P, seconds, seed = args
+    sys.path.insert(0, path)
+    import random
+
+    from splendor.agents.generic.random import myAgent
+    from splendor.splendor.splendor_model import SplendorGameRule
+
+    random.seed(seed)
+    steps = games = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        rule = SplendorGameRule(P)
+        agents = [myAgent(i) for i in range(P)]
+        while not rule.gameEnds():
+            i = rule.getCurrentAgentIndex()
+            actions = rule.getLegalActions(rule.current_game_state, i)
+            rule.update(agents[i].SelectAction(actions, rule.current_game_state, rule))
+            steps += 1
+        games += 1
+    return steps, games, time.perf_counter() - t0
+
+
+def python_engine_throughput(P, seconds=12.0):
+    """The reference's own Python engine on every host core of THIS box, in the same run (north_star: "the reference's
+    Python engine timed on the same box's host cores in the same run, with the core count stated").  None if absent."""
+    for path in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference/src"):
+        if os.path.isdir(os.path.join(path, "splendor", "splendor")):
+            break
+    else:
+        return {"python_reference": "absent on this box"}
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    try:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            res = pool.map(_python_engine_worker, [(path, P, seconds, 1000 + i) for i in range(cores)])
+    except Exception as exc:  # a reported baseline must never fail the line
+        return {"python_reference": "failed: " + repr(exc)[:200]}
+    steps, games = sum(r[0] for r in res), sum(r[1] for r in res)
+    dt = max(r[2] for r in res)
+    return {"value": steps / dt, "unit": UNIT, "cores": cores, "per_core": steps / dt / cores, "kind": "reference",
+            "sample": f"unmodified SplendorGameRule + RandomAgent loop from {os.path.relpath(path, ROOT) if path.startswith(ROOT) else path}, "
+                      f"{games} games ({steps} env-steps) in {dt:.1f} s on {cores} processes"}
+
+
 def run_reference(args):
+    """The CPU arm on the SAME config as the B200 arm: every step plays the same `games_per_gpu` games (same seed, same
+    global game ids as rank 0 of the B200 arm) with the C restatement of the reference engine on all host threads."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return None
-    P = args.players
-    sample_games = 8192
+    P, G, K, W = args.players, args.games_per_gpu, args.steps, max(args.warmup, 3)
+    world = max(int(os.environ.get("WORLD_SIZE", args.gpus)), 1)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
     import oracle as O
 
     O.build()
     cores = os.cpu_count() or 1
-    for w in range(args.warmup):
+    first_game = lambda step: (step * world) * G  # rank 0's slices of the B200 arm
+    for w in range(min(W, 3)):
         O.playout_many(SEED, 10**9 + w * 512, 512, P, False, MAX_STEPS, nthreads=cores, want_outputs=False)
-    total_steps, t0 = 0, time.perf_counter()
-    for k in range(args.steps):
-        _, _, ctr = O.playout_many(SEED, k * sample_games, sample_games, P, False, MAX_STEPS, nthreads=cores, want_outputs=False)
-        total_steps += int(ctr[1])
+    total = np.zeros(16, np.int64)
+    t0 = time.perf_counter()
+    for k in range(K):
+        _, _, ctr = O.playout_many(SEED, first_game(W + k), G, P, False, MAX_STEPS, nthreads=cores, want_outputs=False)
+        total += ctr
     dt = time.perf_counter() - t0
-    value = total_steps / dt
-    sample = f"{sample_games} of the {args.games_per_gpu} games of each step ({args.steps} steps, {total_steps} env-steps, {dt:.1f} s)"
+    c = dict(zip(("games", "steps", "wins0", "wins1", "wins2", "wins3", "ties0", "ties1", "ties2", "ties3", "end_score", "end_deadlock",
+                  "end_roundcap", "end_truncated", "score2_sum", "nobles"), (int(x) for x in total)))
+    value = c["steps"] / dt
+    sample = f"all {G} games of each of the {K} steps (rank 0's game ids), {c['steps']} env-steps in {dt:.1f} s on {cores} host threads"
     return json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * dt / max(K, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "players": P, "envs_per_gpu": args.games_per_gpu,
-                   "note": "CPU arm: C port of the reference's Python engine (oracle/), bit-exact with it on the golden recordings; "
-                           "the Python engine itself ran at ~350 env-steps/s/core here (BASELINE.md)"},
+        "config": config_block(P, G, c),
+        "note": "CPU arm: C port of the reference's Python engine (oracle/), bit-exact with it on the golden recordings, all host "
+                "threads; the Python engine itself is timed in the B200 arm's cpu_baseline_python",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
+
+
+def config_block(P, G, c):
+    """The `config` object, identical in both arms for the same games (the engines are bit-exact, so are the counters)."""
+    return {"workload": WORKLOAD, "players": P, "envs_per_gpu": G, "seed": SEED,
+            "games": c["games"], "env_steps": c["steps"], "mean_game_len": c["steps"] / max(c["games"], 1),
+            "l2": "256 MiB flush write between timed iterations; the fused kernel reads no HBM inputs",
+            "win_rate_seat0": c["wins0"] / max(c["games"], 1), "win_rate_seat1": c["wins1"] / max(c["games"], 1),
+            "ties": c["ties0"], "endings": {k: c[k] for k in ("end_score", "end_deadlock", "end_roundcap", "end_truncated")}}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -240,6 +309,56 @@ def other_sizes(pkg, dev, reps=5):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ configs[4]: the sweep
+SWEEP_GAMES = 1 << 24
+SWEEP_FIRST_GAME = 1 << 44  # game ids of the sweep (disjoint from the bench steps')
+SWEEP_LAUNCH = 1 << 20      # games per launch
+
+
+def run_sweep(pkg, lib, D, dev, stream, rank, world, P):
+    """2^24 two-player games, ids SWEEP_FIRST_GAME .. +2^24, rank r plays the contiguous slice dist.shard_range gives it, in
+    launches of 2^20 games.  Timed by wall clock from before the first launch to after the all-reduce of the counter block has
+    COMPLETED on every rank (max over ranks).  The counters do not depend on N; they are compared with the single-GPU
+    result committed in tests/golden/sweep_counters.json (itself equal to the oracle's, tools/full_size_check.py)."""
+    import torch
+
+    lo, hi = D.shard_range(SWEEP_GAMES, rank, world)
+    ctr = torch.zeros(16, dtype=torch.int64, device=dev)
+
+    def play(c):
+        g = lo
+        while g < hi:
+            n = min(SWEEP_LAUNCH, hi - g)
+            pkg._native.check(lib.spl_playout(SEED, SWEEP_FIRST_GAME + g, n, P, 0, MAX_STEPS, None, None, None, c.data_ptr(), None, 0, None, stream), "spl_playout")
+            g += n
+
+    warm = torch.zeros_like(ctr)
+    pkg._native.check(lib.spl_playout(SEED, SWEEP_FIRST_GAME, min(SWEEP_LAUNCH, hi - lo), P, 0, MAX_STEPS, None, None, None, warm.data_ptr(), None, 0, None, stream), "spl_playout")
+    D.allreduce_counters(warm)  # the communicator is warm before the clock starts
+    torch.cuda.synchronize(dev); D.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    t0 = time.perf_counter()
+    e0.record()
+    play(ctr)
+    e1.record()
+    D.allreduce_counters(ctr)
+    e2.record()
+    torch.cuda.synchronize(dev)
+    wall_ms = D.allreduce_max((time.perf_counter() - t0) * 1e3, dev)
+    kernels_ms = D.allreduce_max(e0.elapsed_time(e1), dev)
+    allreduce_ms = D.allreduce_max(e1.elapsed_time(e2), dev)
+    c = pkg.counters_dict(ctr)
+    want_path = os.path.join(ROOT, "tests", "golden", "sweep_counters.json")
+    equal = None
+    if P == 2 and os.path.exists(want_path):
+        equal = json.load(open(want_path))["counters"] == c
+    return {"workload": "configs[4]: 2^24-game 2-player playout sweep, split over the ranks by global game id", "games": c["games"],
+            "env_steps": c["steps"], "wall_ms": wall_ms, "kernels_ms": kernels_ms, "allreduce_ms": allreduce_ms,
+            "env_steps_per_s": c["steps"] / (wall_ms * 1e-3), "scaling": "strong", "n_gpus": world, "counters_equal_n1": equal,
+            "roofline_frac_per_gpu": c["steps"] / (kernels_ms * 1e-3) * BYTES_PER_STEP / 1e9 / 6533.8 / world,
+            "timing": "wall clock, first launch -> completed NCCL all-reduce of the int64[16] counters, max over ranks"}
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import numpy as np
@@ -314,7 +433,7 @@ def run_b200(args):
                    "note": "this rank only; K launches alternating on two CUDA streams, CUDA-event timed, no L2 flush (the kernel reads no HBM inputs)"}
 
     # ---- end to end through the host-buffer C ABI: host deck orders in, host results out, copies inside the timed region
-    n_sets = min(K + W, 4)
+    n_sets = min(K + W, 32)  # one pinned input set per step (distinct game slices) up to 32 steps, then they repeat
     host_in = []
     for s in range(n_sets):
         eng_lists = torch.empty((G, 90), dtype=torch.uint8, device=dev)
@@ -322,6 +441,7 @@ def run_b200(args):
         st = torch.empty(pkg.state.state_shape(G, P), dtype=torch.int32, device=dev)
         pkg._native.check(lib.spl_reset(st.data_ptr(), SEED, first_game(10_000 + s), None, None, G, P, eng_lists.data_ptr(), eng_nobles.data_ptr(), stream), "spl_reset")
         host_in.append((eng_lists.cpu().pin_memory(), eng_nobles.cpu().pin_memory()))
+        del eng_lists, eng_nobles, st
     # two batches in flight (spl_playout_host_async on alternating slots and streams), as a rollout loop that prepares
     # batch k+1 while batch k plays would run it: every step's H2D and D2H copies are inside the timed region; each step's
     # results are in pinned host memory when its stream reaches the end of the step, and all of them before the clock stops
@@ -362,6 +482,10 @@ def run_b200(args):
     D.allreduce_counters(e2e_steps)
     e2e_value = int(e2e_steps.item()) / e2e_s
 
+    # ---- BASELINE.json configs[4]: the 2^24-game sweep split over the ranks by global game id (strong scaling).  Wall clock
+    # from the first launch to the COMPLETED all-reduce of the counter block: the collective is inside the timed region.
+    sweep = run_sweep(pkg, lib, D, dev, stream, rank, world, P)
+
     other = sizes = None
     if rank == 0:
         try:
@@ -389,27 +513,27 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "players": P, "envs_per_gpu": G, "seed": SEED,
-                   "games": c["games"], "env_steps": total_steps, "mean_game_len": total_steps / max(c["games"], 1),
-                   "l2": "256 MiB flush write between timed iterations; the fused kernel reads no HBM inputs",
-                   "win_rate_seat0": c["wins0"] / max(c["games"], 1), "win_rate_seat1": c["wins1"] / max(c["games"], 1),
-                   "ties": c["ties0"], "endings": {k: c[k] for k in ("end_score", "end_deadlock", "end_roundcap", "end_truncated")}},
+        "config": config_block(P, G, c),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 95, "d2h_bytes_per_step": G * (P + 3) + 128,
-                "path": "spl_playout_host_async, two batches in flight: host deck orders + nobles -> H2D -> inject -> playout -> scores/steps/endings/counters D2H"},
+                "path": "spl_playout_host_async, two batches in flight: host deck orders + nobles -> 2 H2D copies -> ONE kernel (games built from "
+                        "their deck orders and played to the end) -> scores/steps/endings/counters D2H; 10 CUDA API calls per batch",
+                "input_sets": n_sets, "inputs_repeat": bool(K + W > n_sets)},
         "gpu_launches": K * world,
         "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak,
-                     "traffic": traffic, "kernel": "playout_kernel<2,true>", "peak_source": peak_src,
+                     "traffic": traffic, "kernel": "playout_pool_kernel<2,FRESH,20>", "peak_source": peak_src,
                      "algorithmic_bytes_per_env_step": BYTES_PER_STEP,
-                     "note": "state lives in registers for the whole game; the limiter is the integer ALU pipe and, at this batch size, the dependent chain of the longest games - not DRAM (DESIGN.md section 6)"},
+                     "note": "games live in shared memory / registers for their whole life; the limiter is the integer ALU pipe and, at this batch size, the latency of the rounds that hold the longest games - not DRAM (DESIGN.md section 6)"},
         "clocks": clock_info,
         "other_kernels": other,
         "other_sizes": sizes,
         "two_streams": two_streams,
+        "sweep": sweep,
     }
     if world == 1 and not args.no_cpu_baseline:
         v, cores, games, steps, dt = cpu_port_throughput(P, args.cpu_seconds)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": f"{games} of the workload's games ({steps} env-steps) in {dt:.1f} s on {cores} host threads"}
+        out["cpu_baseline_python"] = python_engine_throughput(P, min(args.cpu_seconds, 15.0))
     return json.dumps(out)
 
 

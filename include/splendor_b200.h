@@ -9,6 +9,10 @@
  *     name ends in _host; `stream` is a cudaStream_t passed as void* (0 = default stream); no hidden host sync
  *     except in the *_host functions;
  *   - return value: SPL_OK (0) or a negative SPL_E_* code; nothing throws across the ABI;
+ *   - devices and threads: every call works on the CURRENT CUDA device (cudaSetDevice before the call); the library's own
+ *     state - the staging memory and events of the *_host calls, the cached SM count, the opt-in to large shared memory -
+ *     is kept PER DEVICE, so one process may drive several GPUs.  Calls may come from several host threads (the *_host
+ *     calls serialise on an internal mutex while they enqueue); spl_last_cuda_error is per thread;
  *   - N = number of environments (games) in the batch, P = players per game (2, 3 or 4);
  *   - action indices are positions in the reference's ALL_ACTIONS list (gym/envs/actions.py:222-237), 0..3509;
  *   - card ids are tier-major (include/spl_tables.h), noble ids index NOBLES, colour ids black0 red1 green2 blue3
@@ -158,12 +162,16 @@ int spl_observe(const void *state, const int8_t *seat, float *obs, int64_t N, in
  * choice (Philox word of (seed, game, step) scaled to the count, k-th legal action in ascending ALL_ACTIONS order)
  * + step + terminal + calScore.  Outputs (all optional): score2 [G][P], steps [G], end_kind [G], counters[16]
  * (accumulated), trace [trace_len][G] = action index taken at step t (-1 after the end), final_state (packed layout,
- * N = num_games).  max_steps in 1..4096. */
+ * N = num_games).  max_steps in 1..4096.
+ * Kernel: playout_pool_kernel - every block owns a pool of games in shared memory, warps play 8 moves of 32 live games
+ * out of registers, then the block compacts the survivors and tops the pool up with new games. */
 int spl_playout(uint64_t seed, uint64_t first_game, int64_t num_games, int P, uint32_t flags, int max_steps,
                 int8_t *score2, int16_t *steps, uint8_t *end_kind, int64_t *counters,
                 int16_t *trace, int trace_len, void *final_state, void *stream);
 
-/* Same, continuing from existing states (e.g. after spl_inject, with `decks`); states are updated in place. */
+/* Same, continuing from existing states (e.g. after spl_inject, with `decks`); states are updated in place.
+ * `steps` and the SPL_CTR_STEPS counter count the moves made by THIS call (a state handed in mid-game does not bring its
+ * earlier turns along); a state that is already terminal is scored with 0 steps. */
 int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
                      int64_t N, int P, uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind,
                      int64_t *counters, int16_t *trace, int trace_len, void *stream);
@@ -189,8 +197,9 @@ int spl_masked_sample(const float *logits, int64_t row_stride, const uint32_t *m
                       const uint64_t *ids, uint32_t step, int greedy, int16_t *action, float *log_prob, int64_t N, void *stream);
 
 /* Host-buffer forms (the end-to-end path a reference-side caller uses): pageable or pinned HOST pointers in and out,
- * device staging buffers owned by the library, copies + kernel + copies on `stream`, then a stream synchronise.
- * deck_lists/nobles as in spl_inject; outputs as in spl_playout. */
+ * device staging buffers owned by the library (per device and slot, grow-only), all work on `stream`: two H2D copies,
+ * ONE kernel that builds every game from its deck order and plays it to the end, four D2H copies - then a stream
+ * synchronise.  deck_lists/nobles as in spl_inject; outputs as in spl_playout. */
 int spl_playout_host(const uint8_t *deck_lists, const uint8_t *nobles, uint64_t seed, uint64_t first_game, int64_t N,
                      int P, uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind,
                      int64_t *counters, void *stream);
@@ -206,7 +215,7 @@ int spl_playout_host_async(const uint8_t *deck_lists, const uint8_t *nobles, uin
                            int P, uint32_t flags, int max_steps, int8_t *score2, int16_t *steps, uint8_t *end_kind,
                            int64_t *counters, int slot, void *stream);
 
-/* Device the library should use for its staging buffers and table upload (default: current device). */
+/* Creates the CUDA context of the current device and caches its properties (optional; every call does it on demand). */
 int spl_warmup(void);
 
 #ifdef __cplusplus

@@ -50,7 +50,7 @@ __device__ __forceinline__ void stage_tables_nosync(Tables &sT)
     for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 16); i += blockDim.x) dst[i] = src[i];
 }
 constexpr int ENV_TB = 256;        // threads per block of the persistent thread-per-env kernels (step, env move)
-constexpr int STEP_BLOCKS_PER_SM = 4, ENV_MOVE_BLOCKS_PER_SM = 3;  // what the register counts (64 / 80) let reside
+constexpr int STEP_BLOCKS_PER_SM = 3, ENV_MOVE_BLOCKS_PER_SM = 3;  // what the register counts (80 each) let reside
 
 // ---------------------------------------------------------------------------------------------- reset / inject
 template <int P>
@@ -326,15 +326,15 @@ __global__ void __launch_bounds__(32 * NW, SPL_POOL_BLOCKS_PER_SM) playout_pool_
 // Persistent: the grid is (SMs x resident blocks), every block stages the tables ONCE and strides over the envs; the first
 // env's action and state loads are issued before the table copy and its barrier.
 template <int P>
-__global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+__global__ void __launch_bounds__(ENV_TB, 3) step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
                                                       const uint64_t *game_ids, const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal,
                                                       int64_t N, uint32_t flags)
 {
     __shared__ __align__(16) Tables sT;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    Env<P> e;
-    int a = -1;
+    Env<P> e, nx;
+    int a = -1, na = -1;
     if (i < N) {
         a = action[i];
         load_env(e, state, N, i);
@@ -342,6 +342,11 @@ __global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_
     stage_tables_nosync(sT);
     __syncthreads();
     while (i < N) {
+        const int64_t ni = i + stride;
+        if (ni < N) {  // the next env's loads are in flight while this one is decoded, applied and stored
+            na = action[ni];
+            load_env(nx, state, N, ni);
+        }
         int rew = 0, bad = 0;
         if (a >= 0) {
             Ctx c;
@@ -359,11 +364,9 @@ __global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_
         if (reward) reward[i] = (int8_t)rew;
         if (illegal) illegal[i] = (uint8_t)bad;
         if (done) done[i] = (uint8_t)game_ends(e, flags);
-        i += stride;
-        if (i < N) {
-            a = action[i];
-            load_env(e, state, N, i);
-        }
+        i = ni;
+        a = na;
+        e = nx;
     }
 }
 

@@ -139,6 +139,14 @@ class SplendorVecEnv:
     the next mover's observation and mask (info["my_id"]), so one policy can play all seats.
     opponent="minimax" (2 players): the opponent is the reference's MiniMaxAgent (agents/our_agents/minmax.py), the default
     PPO test opponent (arguments_parsing.py:107), searched on the GPU for all envs at once (spl_minimax2).
+    opponent=<callable>: every seat that is not the learner's is played by a (frozen) POLICY, as the reference does for
+    `--opponent itself` and for saved PPO opponents (ppo/ppo.py:176-196: PPOAgent objects that share or load a network;
+    ppo_agent.py:32-64: observation of the agent's own seat -> masked network -> arg-max).  The callable receives
+    (obs float32 [N,265] of the seats to move, packed legal masks int32 [N,110], seats int8 [N]) for ALL envs and returns
+    either float32 logits [N,>=3510] - the opponent then takes the arg-max over its legal actions (opponent_greedy=True, the
+    reference's behaviour) or a masked categorical sample (opponent_greedy=False; spl_masked_sample keyed by the env's game
+    id and turn) - or an int16 [N] tensor of action indices.  Rows of envs that are at their learner or already over are
+    ignored.  Everything stays on the device; a call makes at most P-1 policy evaluations.
 
     reset()  -> (obs [N,265] f32, {"my_id": int8 [N]})
     step(a)  -> (obs, reward f32 [N], terminated bool [N], truncated bool [N] (always False), info)
@@ -150,12 +158,17 @@ class SplendorVecEnv:
 
     def __init__(self, num_envs: int, num_agents: int = 2, seed: int = 1234, first_game: int = 0, shuffle_turns: bool = True,
                  fixed_turn: int | None = None, device="cuda", raise_on_illegal: bool = False, self_play: bool = False,
-                 opponent: str = "random"):
-        if opponent not in ("random", "minimax"):
+                 opponent="random", opponent_greedy: bool = True):
+        if not callable(opponent) and opponent not in ("random", "minimax"):
             raise ValueError(f"unknown opponent {opponent!r}")
         if opponent == "minimax" and (num_agents != 2 or self_play):
             raise ValueError("the minimax opponent supports only a game of 2 players (and no self-play)")
-        self.opponent = opponent
+        if callable(opponent) and self_play:
+            raise ValueError("a policy opponent and self_play exclude each other (self_play already hands every seat to the caller)")
+        self.opponent = "policy" if callable(opponent) else opponent
+        self.opponent_policy = opponent if callable(opponent) else None
+        self.opponent_greedy = opponent_greedy
+        self.opponent_seed = seed
         self.num_envs, self.number_of_players = int(num_envs), int(num_agents)
         self.engine = BatchedSplendor(num_envs, num_agents, seed=seed, first_game=first_game, limit_rounds=True, device=device)
         self.device = self.engine.device
@@ -170,6 +183,7 @@ class SplendorVecEnv:
         self._episode = torch.zeros(num_envs, dtype=torch.int64, device=self.device)
         self._ids = None
         self._done = torch.zeros(num_envs, dtype=torch.bool, device=self.device)
+        self._policy_calls = 0  # the `step` key of the opponents' sampled draws (with the env's game id)
         self.my_turn = torch.zeros(num_envs, dtype=torch.int8, device=self.device)
         self.legal_mask = None
 
@@ -192,6 +206,8 @@ class SplendorVecEnv:
         skip = torch.full((self.num_envs,), -1, dtype=torch.int16, device=self.device)
         if self.opponent == "minimax":
             self._minimax_opponents_move()
+        elif self.opponent == "policy":
+            self._policy_opponents_move()
         obs, _, term, _, mask = self.engine.env_step(self.my_turn, skip, self_play=self.self_play)
         if self.self_play:
             self.my_turn = self._seat_to_move()
@@ -220,10 +236,13 @@ class SplendorVecEnv:
             self.my_turn = self.my_turn.clone()
             self.my_turn[self._done] = self._draw_seats(n).to(self.device)
             a = torch.where(self._done, torch.full_like(a, -1), a)
-        if self.opponent == "minimax":
-            # the learner's move alone (it is the seat to move wherever a >= 0), the searched reply, then the learner's rows
+        if self.opponent in ("minimax", "policy"):
+            # the learner's move alone (it is the seat to move wherever a >= 0), the opponents' replies, then the learner's rows
             _, reward, _, illegal, _ = self.engine.env_step(None, a, want_mask=False, want_obs=False, self_play=True)
-            self._minimax_opponents_move()
+            if self.opponent == "minimax":
+                self._minimax_opponents_move()
+            else:
+                self._policy_opponents_move()
             skip = torch.full_like(a, -1)
             obs, _, term, _, mask = self.engine.env_step(self.my_turn, skip)
         else:
@@ -247,6 +266,28 @@ class SplendorVecEnv:
         if bool(need.any()):
             best = self.engine.minimax2()[0]
             self.engine.env_step(None, torch.where(need, best, skip), want_mask=False, want_obs=False, self_play=True)
+
+    def _policy_opponents_move(self):
+        """_simulate_opponents (splendor_env.py:219-231) with policy-driven agents: until every env is back at its learner
+        or over, the seats to move get their own observation and mask, the policy answers, the moves are applied."""
+        from .sampling import masked_sample
+
+        skip = torch.full((self.num_envs,), -1, dtype=torch.int16, device=self.device)
+        for _ in range(self.number_of_players - 1):
+            obs, _, term, _, mask = self.engine.env_step(None, skip, self_play=True)  # rows of the seats to move
+            seats = self._seat_to_move()
+            need = (term == 0) & (seats != self.my_turn)
+            if not bool(need.any()):
+                break
+            out = self.opponent_policy(obs, mask, seats)
+            if out.dtype in (torch.int16, torch.int32, torch.int64):
+                actions = out.to(torch.int16)
+            else:
+                step = int(self._policy_calls)
+                actions, _ = masked_sample(out.to(torch.float32).contiguous(), mask, self.opponent_seed, step, ids=self._ids,
+                                           greedy=self.opponent_greedy, want_log_prob=False)
+            self._policy_calls += 1
+            self.engine.env_step(None, torch.where(need, actions, skip), want_mask=False, want_obs=False, self_play=True)
 
     def _seat_to_move(self) -> torch.Tensor:
         return ((self.engine.state[1, :, 3] >> 20) & 3).to(torch.int8)

@@ -166,3 +166,62 @@ def test_dropin_env_class_replays_scripted_episodes(pkg, monkeypatch):
             assert np.array_equal(np.nonzero(env.get_legal_actions_mask())[0], e["legal"][c]), (gi, c)
         with pytest.raises(ValueError):
             env.step(3510)
+
+
+def test_policy_opponents_match_oracle_emulation(pkg, oracle):
+    """SplendorVecEnv(opponent=policy_fn): the seats that are not the learner's are moved by a frozen policy on the device
+    (reference: ppo/ppo.py:176-196 + ppo_agent.py:32-64 - own-seat observation, masked network, arg-max).  The policy here
+    has exactly reproducible integer logits, a function of the agent's turn count (observation entry 1) and the action
+    index; the whole vector env - auto-reset included - is followed by an oracle emulation for three players."""
+    N, P, seed, seat = 48, 3, 77, 1
+    idx = torch.arange(3510, device="cuda", dtype=torch.int64)
+
+    def policy(obs, mask, seats):
+        turn = obs[:, 1].to(torch.int64)
+        return ((idx[None, :] * 7919 + turn[:, None] * 104729) % 1009).to(torch.float32)
+
+    def opponent_choice(s):
+        legal = oracle.legal(s).astype(np.int64)
+        vals = (legal * 7919 + int(s.pl[s.cur].turns) * 104729) % 1009
+        return int(legal[int(np.argmax(vals))])  # first maximum = lowest index, as the arg-max of spl_masked_sample
+
+    venv = pkg.SplendorVecEnv(N, P, seed=seed, first_game=500, fixed_turn=seat, opponent=policy)
+    episode = np.zeros(N, np.int64)
+    orcs = [oracle.init(P, *oracle.synth_game(seed, 500 + e, P)) for e in range(N)]
+
+    def opponents(e):
+        s = orcs[e]
+        while s.cur != seat and not oracle.game_ends(s, True):
+            oracle.step(s, opponent_choice(s))
+
+    obs, info = venv.reset()
+    for e in range(N):
+        opponents(e)
+    rng = np.random.default_rng(3)
+    done = np.zeros(N, bool)  # the game of env e ended at the previous step: the next step auto-resets it and ignores the action
+    finished = 0
+    for it in range(75):
+        o, m = obs.cpu().numpy(), info["legal_mask"].cpu().numpy()
+        act = np.zeros(N, np.int16)
+        for e in range(N):
+            legal = oracle.legal(orcs[e], seat)
+            assert np.array_equal(unpack_mask(m[e]), legal), (e, it)
+            assert np.array_equal(o[e].view(np.uint32), oracle.observe(orcs[e], seat).view(np.uint32)), (e, it)
+            act[e] = rng.choice(legal)
+        obs, reward, term, trunc, info = venv.step(torch.from_numpy(act))
+        reward, term = reward.cpu().numpy(), term.cpu().numpy()
+        for e in range(N):
+            if done[e]:  # auto-reset: a new game id, the opponents seated before the learner move, no reward
+                episode[e] += 1
+                orcs[e] = oracle.init(P, *oracle.synth_game(seed, 500 + e + episode[e] * N, P))
+                opponents(e)
+                assert reward[e] == 0 and not term[e], (e, it)
+                done[e] = False
+                continue
+            assert reward[e] == oracle.step(orcs[e], int(act[e])), (e, it)
+            opponents(e)
+            assert bool(term[e]) == (oracle.game_ends(orcs[e], True) != 0), (e, it)
+            if term[e]:
+                done[e] = True
+                finished += 1
+    assert finished >= N // 2

@@ -180,6 +180,103 @@ def test_properties_at_full_size_4p(pkg):
     assert torch.equal(h0["counters"] + h1["counters"], a["counters"])
 
 
+def sampled_blocks(total, n_blocks, block):
+    """n_blocks contiguous runs of `block` game indices spread evenly over [0, total) (the first and the last run included)."""
+    return [int(round(i * (total - block) / (n_blocks - 1))) for i in range(n_blocks)]
+
+
+def test_full_size_4p_sample_is_exact(pkg, oracle):
+    """Config 3 at full size (2^20 four-player games in ONE launch): 16,384 games sampled in 64 runs across the launch have
+    exactly the oracle's length, scores and ending (about 2.7 M oracle steps)."""
+    G, P, seed, first = 1 << 20, 4, 5, 0
+    a = pkg.playout_games(G, P, seed=seed, first_game=first)
+    steps, score2, kind = a["steps"].cpu().numpy(), a["score2"].cpu().numpy(), a["end_kind"].cpu().numpy()
+    checked = 0
+    for lo in sampled_blocks(G, 64, 256):
+        sc, st, ctr = oracle.playout_many(seed, first + lo, 256, P, False, 1000, nthreads=os.cpu_count() or 1)
+        assert np.array_equal(steps[lo:lo + 256].astype(np.int32), st) and np.array_equal(score2[lo:lo + 256], sc), lo
+        assert int((kind[lo:lo + 256] == 1).sum()) == int(ctr[10]) and int((kind[lo:lo + 256] == 2).sum()) == int(ctr[11]), lo
+        checked += 256
+    assert checked == 16_384
+
+
+def test_sweep_2p_2_24_games_counters_and_sample_are_exact(pkg, oracle):
+    """Config 5 at full size: the 2^24-game two-player sweep of bench.py (same seed and game ids, 16 launches of 2^20):
+    all 16 counters equal tests/golden/sweep_counters.json - computed by the ORACLE over all 2^24 games
+    (tools/sweep_oracle.py) - and 32,768 games sampled in 128 runs have exactly the oracle's length, scores and ending."""
+    import json
+
+    from conftest import GOLDEN
+
+    G, P, seed, first, per = 1 << 24, 2, 1234, 1 << 44, 1 << 20
+    ctr = torch.zeros(16, dtype=torch.int64, device="cuda")
+    steps = torch.empty(G, dtype=torch.int16, device="cuda")
+    score2 = torch.empty((G, P), dtype=torch.int8, device="cuda")
+    kind = torch.empty(G, dtype=torch.uint8, device="cuda")
+    lib = pkg._native.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    for lo in range(0, G, per):
+        rc = lib.spl_playout(seed, first + lo, per, P, 0, 1000, score2[lo:].data_ptr(), steps[lo:].data_ptr(), kind[lo:].data_ptr(),
+                             ctr.data_ptr(), None, 0, None, stream)
+        assert rc == 0
+    c = pkg.counters_dict(ctr)
+    assert c["games"] == G and c["steps"] == int(steps.to(torch.int64).sum()) and c["score2_sum"] == int(score2.to(torch.int64).sum())
+    want = json.load(open(os.path.join(GOLDEN, "sweep_counters.json")))
+    assert (want["seed"], want["first_game"], want["games"]) == (seed, first, G)
+    assert c == want["counters"]
+    steps, score2, kind = steps.cpu().numpy(), score2.cpu().numpy(), kind.cpu().numpy()
+    for lo in sampled_blocks(G, 128, 256):
+        sc, st, octr = oracle.playout_many(seed, first + lo, 256, P, False, 1000, nthreads=os.cpu_count() or 1)
+        assert np.array_equal(steps[lo:lo + 256].astype(np.int32), st) and np.array_equal(score2[lo:lo + 256], sc), lo
+        assert int((kind[lo:lo + 256] == 1).sum()) == int(octr[10]), lo
+
+
+def test_env_step_at_full_size_sample_is_exact(pkg, oracle):
+    """Config 4 at full size: spl_env_step on 262,144 two-player envs for 32 calls (reset call + 31 learner moves chosen on
+    the device from the returned masks); 4,096 envs sampled in 32 runs are followed by the oracle's emulation of
+    SplendorEnv (learner move, Philox opponents, 100-round cap) and compared EVERY call: reward, terminated, legal set,
+    observation bits - and the full state after the last call."""
+    N, P, seed = 262_144, 2, 4321
+    rng = np.random.default_rng(9)
+    learner_np = rng.integers(0, P, N).astype(np.int8)
+    learner = torch.from_numpy(learner_np).cuda()
+    eng = pkg.BatchedSplendor(N, P, seed=seed, first_game=0, limit_rounds=True)
+    sample = np.concatenate([np.arange(lo, lo + 128) for lo in sampled_blocks(N, 32, 128)])
+    orcs = {int(e): oracle.init(P, *oracle.synth_game(seed, int(e), P)) for e in sample}
+
+    def opponents(e):
+        s = orcs[e]
+        while s.cur != learner_np[e] and not oracle.game_ends(s, True):
+            legal = oracle.legal(s)
+            t = sum(s.pl[i].turns for i in range(P))
+            r = int(oracle.philox(seed, e, t, 0)[0])
+            oracle.step(s, int(legal[(r * len(legal)) >> 32]))
+
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    act = torch.full((N,), -1, dtype=torch.int16, device="cuda")
+    sample_t = torch.from_numpy(sample).cuda()
+    for call in range(32):
+        obs, reward, term, illegal, mask = eng.env_step(learner, act)
+        assert int(illegal.sum()) == 0
+        a_np = act[sample_t].cpu().numpy()
+        o_np, r_np, t_np, m_np = obs[sample_t].cpu().numpy(), reward[sample_t].cpu().numpy(), term[sample_t].cpu().numpy(), mask[sample_t].cpu().numpy()
+        for j, e in enumerate(sample):
+            e = int(e)
+            if a_np[j] >= 0:
+                assert r_np[j] == oracle.step(orcs[e], int(a_np[j])), (e, call)
+            opponents(e)
+            assert t_np[j] == oracle.game_ends(orcs[e], True), (e, call)
+            assert np.array_equal(unpack_mask(m_np[j]), oracle.legal(orcs[e], int(learner_np[e]))), (e, call)
+            assert np.array_equal(o_np[j].view(np.uint32), oracle.observe(orcs[e], int(learner_np[e])).view(np.uint32)), (e, call)
+        # next actions, on the device: a uniformly random legal action where the game goes on, "skip" where it is over
+        bits = ((mask.unsqueeze(-1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1).reshape(N, -1)[:, :3510].to(torch.float32)
+        pick = torch.multinomial(bits, 1, generator=gen).squeeze(1).to(torch.int16)
+        act = torch.where(term != 0, torch.full_like(pick, -1), pick)
+    sn = pkg.state.snapshots(eng.state[:, sample_t].cpu().numpy().view(np.uint32), P)
+    for j, e in enumerate(sample):
+        assert np.array_equal(sn[j], orcs[int(e)].snapshot()), e
+
+
 def test_illegal_actions_are_flagged_and_ignored(pkg, oracle):
     N, P = 256, 2
     eng = pkg.BatchedSplendor(N, P, seed=3)
