@@ -528,10 +528,12 @@ struct Ctx {
     bool bank_yellow;
 };
 
-template <int P>
+// MOVER0: the caller keeps the player words ROTATED so that the seat to move is always entry 0 (the playout kernel does:
+// a rotation is a handful of register moves per move, the per-seat selects it replaces are ~4 P compare/select pairs)
+template <int P, bool MOVER0 = false>
 __device__ __forceinline__ void make_ctx(const Env<P> &e, const Tables &T, Ctx &c)
 {
-    const int seat = seat_of(e.meta);
+    const int seat = MOVER0 ? 0 : seat_of(e.meta);
     c.gems = e.pg[0]; c.cards = e.pc[0]; c.resv = e.pr[0];
 #pragma unroll
     for (int p = 1; p < P; p++)
@@ -916,14 +918,14 @@ __device__ __forceinline__ bool decode_and_check(const Env<P> &e, const Tables &
 
 // ------------------------------------------------------------------------------------------------ successor
 // generateSuccessor + GameRule.update.  Returns the acting agent's score delta.
-template <int P, bool LISTS = false>
+template <int P, bool LISTS = false, bool MOVER0 = false>
 __device__ __forceinline__ int apply_action(Env<P> &e, const Choice &ch, const DeckSrc &src)
 {
-    const int seat = seat_of(e.meta);
+    const int seat = seat_of(e.meta), slot = MOVER0 ? 0 : seat;  // slot: where the mover's words are
     uint32_t g = e.pg[0], cd = e.pc[0], rv = e.pr[0], pi = e.pi[0];
 #pragma unroll
     for (int p = 1; p < P; p++)
-        if (seat == p) { g = e.pg[p]; cd = e.pc[p]; rv = e.pr[p]; pi = e.pi[p]; }
+        if (slot == p) { g = e.pg[p]; cd = e.pc[p]; rv = e.pr[p]; pi = e.pi[p]; }
 
     SPL_CHECK(satsub6(ch.R, g + ch.C) == 0 && satsub6(ch.C, e.bank + ch.R) == 0);  // nobody pays or takes gems that are not there
     g = g + ch.C - ch.R;
@@ -959,10 +961,31 @@ __device__ __forceinline__ int apply_action(Env<P> &e, const Choice &ch, const D
     pi = ((pi + 1u) & ~(1u << 26)) | (ch.type == T_PASS ? 1u << 26 : 0u);
 #pragma unroll
     for (int p = 0; p < P; p++)
-        if (seat == p) { e.pg[p] = g; e.pc[p] = cd; e.pr[p] = rv; e.pi[p] = pi; }
+        if (slot == p) { e.pg[p] = g; e.pc[p] = cd; e.pr[p] = rv; e.pi[p] = pi; }
     const int next = seat + 1 == P ? 0 : seat + 1;
     e.meta = (e.meta & ~(3u << 20)) | ((uint32_t)next << 20);
     return score;
+}
+
+// player words one place to the left (entry 1 becomes entry 0): after a move of a MOVER0 state the next mover is in front
+template <int P>
+__device__ __forceinline__ void rotate_players_left(Env<P> &e)
+{
+    const uint32_t g = e.pg[0], c = e.pc[0], r = e.pr[0], i = e.pi[0];
+#pragma unroll
+    for (int p = 0; p + 1 < P; p++) { e.pg[p] = e.pg[p + 1]; e.pc[p] = e.pc[p + 1]; e.pr[p] = e.pr[p + 1]; e.pi[p] = e.pi[p + 1]; }
+    e.pg[P - 1] = g; e.pc[P - 1] = c; e.pr[P - 1] = r; e.pi[P - 1] = i;
+}
+// seat-order state <-> MOVER0 state (entry 0 = the seat to move, entry k = seat (seat + k) mod P)
+template <int P>
+__device__ __forceinline__ void to_mover_first(Env<P> &e)
+{
+    for (int k = seat_of(e.meta); k > 0; k--) rotate_players_left(e);
+}
+template <int P>
+__device__ __forceinline__ void to_seat_order(Env<P> &e)
+{
+    for (int k = (P - seat_of(e.meta)) % P; k > 0; k--) rotate_players_left(e);
 }
 
 // generatePredecessor (splendor_model.py:156-220): undo ALL_ACTIONS[idx] for `seat`.  `card` = the card that was bought
