@@ -1150,10 +1150,15 @@ __device__ __forceinline__ uint64_t times_nobles(uint32_t variants, int V, uint3
 // `done(w0, w1)` is called as soon as words [w0, w1) (even bounds) are final, in ascending order and covering 0..110 with
 // [0, 2) last: a kernel stores them right away, so only a quarter of the row is ever live in registers.
 struct MaskKeep { __device__ __forceinline__ void operator()(int, int) const {} };
-template <int P, class Done = MaskKeep>
+// NO_S: the caller guarantees c.S == 0 (no noble is waiting: true for almost every decision - a noble is claimed with the
+// action that earns it, c.S != 0 needs two nobles earned at once).  Then every collect / reserve action carries noble slot 0
+// only, the (noble x variant) patterns are the variant bits themselves, and the 64-bit shift / select chains of
+// times_nobles fold away at compile time (they were 14 % of the mask kernel's instructions, profiles/r2_kernels.md).
+template <int P, class Done = MaskKeep, bool NO_S = false>
 __device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &T, const Ctx &c, uint32_t *m, Done done = Done())
 {
-    const uint32_t NP = c.S ? c.S << 1 : 1u;
+    SPL_CHECK(!NO_S || c.S == 0);
+    const uint32_t NP = NO_S ? 1u : (c.S ? c.S << 1 : 1u);
     bool any = false;
     // reserve (:498-520): the same 42-bit (noble x variant) pattern for every occupied slot
     if (c.n_resv < 3 && c.occ) {

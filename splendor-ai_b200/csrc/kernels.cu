@@ -589,11 +589,21 @@ __device__ __forceinline__ void obs_tile_store(const uint8_t *wtile, float *out,
     for (int j = 0; j < n; j++) {
         const uint8_t *row = wtile + j * OBS_ROW_BYTES;
         float *dst = out + (int64_t)j * SPL_OBS_SIZE;
-        dst[lane] = obs_entry(row, lane, g_log1p_bits);  // the three special entries (turns, variance, log table) are all < 32
 #pragma unroll
-        for (int k = 1; k < FULL; k++) dst[lane + 32 * k] = byte_to_float(row[lane + 32 * k]);
+        for (int k = 0; k < FULL; k++) dst[lane + 32 * k] = byte_to_float(row[lane + 32 * k]);  // (the 7 special entries: obs_patch_special)
         if (lane < SPL_OBS_SIZE - 32 * FULL) dst[lane + 32 * FULL] = byte_to_float(row[lane + 32 * FULL]);
     }
+}
+// The seven entries of a row that are not plain bytes - turns [1], the variance [6] (one IEEE division), log(1 + buying
+// power) [19..23] - are written by the lane that OWNS the row, all 32 lanes at once, after the warp's plain stores.  Round 1
+// decoded them inside the row loop: the division's slow path ran once per ROW at one active lane (12 % of the kernel's
+// instructions, 24 % with the other two cases; profiles/r2_kernels.md).
+__device__ __forceinline__ void obs_patch_special(const uint8_t *row, float *dst)
+{
+    dst[1] = obs_entry(row, 1, g_log1p_bits);
+    dst[6] = obs_entry(row, 6, g_log1p_bits);
+#pragma unroll
+    for (int w = 19; w < 24; w++) dst[w] = obs_entry(row, w, g_log1p_bits);
 }
 struct ObsRowSink {
     uint32_t *row;
@@ -629,7 +639,10 @@ __global__ void __launch_bounds__(TILE_TB_MAX) legal_mask_kernel(const uint4 *st
             uint32_t m[MASK_REGS];
 #pragma unroll
             for (int w = 0; w < MASK_REGS; w++) m[w] = 0;
-            thread_fill_mask(e, sT, c, m, MaskRowSink{reinterpret_cast<uint2 *>(wtile + lane * SPL_MASK_WORDS), m});
+            const MaskRowSink sink{reinterpret_cast<uint2 *>(wtile + lane * SPL_MASK_WORDS), m};
+            // warp-uniform choice: the general row builder only if some env of this group has a noble waiting (rare)
+            if (__all_sync(__activemask(), c.S == 0)) thread_fill_mask<P, MaskRowSink, true>(e, sT, c, m, sink);
+            else thread_fill_mask<P, MaskRowSink, false>(e, sT, c, m, sink);
         }
         mask_tile_store(wtile, mask + base * SPL_MASK_WORDS, (int)min((int64_t)32, N - base), lane);
     }
@@ -655,6 +668,8 @@ __global__ void __launch_bounds__(TILE_TB_MAX) observe_kernel(const uint4 *state
         }
         __syncwarp();
         obs_tile_store(reinterpret_cast<const uint8_t *>(wtile), obs + base * SPL_OBS_SIZE, (int)min((int64_t)32, N - base), lane);
+        __syncwarp();  // orders the plain stores of every lane before the owners' patches of the same addresses
+        if (i < N) obs_patch_special(reinterpret_cast<const uint8_t *>(wtile) + lane * OBS_ROW_BYTES, obs + i * SPL_OBS_SIZE);
         __syncwarp();
     }
 }
