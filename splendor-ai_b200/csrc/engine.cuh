@@ -595,6 +595,38 @@ __device__ __forceinline__ uint32_t same_variant_bits(const Tables &T, const Ctx
     return e2 <= 0 ? 1u : (e2 == 1 ? x << 11 : ((uint32_t)T.pairs5[x] << 1 | y << 16));
 }
 
+// The same two functions for a caller that evaluates MANY groups of one env (the mask row builder): the case "how many gems
+// must go back" is the same for all groups of a size, so it is turned into AND-masks once and every group becomes a short
+// branch-free sequence (lookups + shifts + AND/OR).  With the nested selects above the compiler emitted a branch region per
+// group, executed at ~9 active lanes: 41 % of the mask kernel's instructions (profiles/r2_kernels.md).
+struct ExSel { uint32_t is0, m1, m2, m3; };  // excess <= 0 -> bit 0 ("return nothing") ; == 1 / 2 / 3 -> all-ones masks
+__device__ __forceinline__ ExSel make_exsel(int ex)
+{
+    return ExSel{ex <= 0 ? 1u : 0u, ex == 1 ? ~0u : 0u, ex == 2 ? ~0u : 0u, ex == 3 ? ~0u : 0u};
+}
+template <int L>
+__device__ __forceinline__ uint32_t diff_variant_bits_sel(const Tables &T, const Ctx &c, int ci, const ExSel &s)
+{
+    constexpr int kk = 6 - L;
+    const uint32_t x = T.pext_diff[ci][c.h1];
+    uint32_t r = s.is0 | ((x << 1) & s.m1);
+    if (L >= 2) {
+        const uint32_t y = T.pext_diff[ci][c.h2];
+        const uint32_t two = (uint32_t)(T.cwr2_pair[L == 2][x & 15u] | T.cwr2_dbl[L == 2][y & 15u]);
+        r |= (two << (1 + kk)) & s.m2;
+        if (L == 3) {
+            const uint32_t z = T.pext_diff[ci][c.h3];
+            r |= ((uint32_t)T.cwr3[x | y << 3 | z << 6] << 10) & s.m3;
+        }
+    }
+    return r;
+}
+__device__ __forceinline__ uint32_t same_variant_bits_sel(const Tables &T, const Ctx &c, int col, const ExSel &s)
+{
+    const uint32_t x = T.pext_same[col][c.h1], y = T.pext_same[col][c.h2];
+    return s.is0 | ((x << 11) & s.m1) | (((uint32_t)T.pairs5[x] << 1 | y << 16) & s.m2);
+}
+
 // resources_sufficient (:371-394): returns true and the payment if the card is affordable and below the 7-card cap
 __device__ __forceinline__ bool can_buy(const Ctx &c, uint2 cw, uint32_t &pay)
 {
@@ -1181,22 +1213,25 @@ __device__ __forceinline__ void thread_fill_mask(const Env<P> &e, const Tables &
     const uint32_t np_lo = NP & 7u, np_hi = NP >> 3;
     uint32_t any_bits = 0;
     {
-        const int e2 = c.hold - 8;
+        const ExSel s2 = make_exsel(c.hold - 8);
 #pragma unroll
         for (int col = 0; col < 5; col++) {
-            const uint32_t vs = (c.A4 >> field_of_normal(col) & 1u) ? same_variant_bits(T, c, col, e2) : 0u;
+            const uint32_t vs = same_variant_bits_sel(T, c, col, s2) & ((c.A4 >> field_of_normal(col) & 1u) ? ~0u : 0u);
             or_bits64(m, BASE_SAME + 126 * col, times_nobles(vs, 21, np_lo));
             if (np_hi) or_bits64(m, BASE_SAME + 126 * col + 63, times_nobles(vs, 21, np_hi));  // nobles at list position >= 2: rare
             any_bits |= vs;
         }
     }
     done(2, 34);  // reserve and collect_same end at bit 1139
+    const ExSel sd1 = make_exsel(c.hold + 1 - 10), sd2 = make_exsel(c.hold + 2 - 10), sd3 = make_exsel(c.hold + 3 - 10);
 #pragma unroll
     for (int ci = 0; ci < 25; ci++) {
         const int L = ci < 5 ? 1 : (ci < 15 ? 2 : 3), V = L == 1 ? 6 : (L == 2 ? 15 : 20);
         const uint32_t cm = T.combo_mask[ci];
         const bool valid = !(cm & ~c.A1) && L >= c.Lmin;
-        const uint32_t vd = valid ? diff_variant_bits(T, c, ci, L, c.hold + L - 10) : 0u;
+        const uint32_t vd_all = L == 1 ? diff_variant_bits_sel<1>(T, c, ci, sd1)
+                                       : (L == 2 ? diff_variant_bits_sel<2>(T, c, ci, sd2) : diff_variant_bits_sel<3>(T, c, ci, sd3));
+        const uint32_t vd = valid ? vd_all : 0u;
         const int base = BASE_DIFF + (L == 1 ? 36 * ci : (L == 2 ? 180 + 90 * (ci - 5) : 1080 + 120 * (ci - 15)));
         if (L == 1) or_bits64(m, base, times_nobles(vd, V, np_lo) | times_nobles(vd, V, np_hi) << 18);
         else {
