@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_
                                                       const uint64_t *game_ids, const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal,
                                                       int64_t N, uint32_t flags)
 {
-    __shared__ __align__(16) Tables sT;
+    __shared__ __align__(16) Tables sT;  // (reading the tables through L1 instead of staging them: no difference, A/B r2r)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Env<P> e;
