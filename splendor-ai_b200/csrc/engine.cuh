@@ -627,6 +627,19 @@ __device__ __forceinline__ uint32_t same_variant_bits_sel(const Tables &T, const
     return s.is0 | ((x << 11) & s.m1) | (((uint32_t)T.pairs5[x] << 1 | y << 16) & s.m2);
 }
 
+// the same for ONE group whose size is only known at run time (select_family): all lookups unconditional, the case picked
+// by masks; entries that do not apply to the size (pairs for L = 1, triples for L < 3) are masked out because the excess
+// cannot reach them (hold <= 10)
+__device__ __forceinline__ uint32_t diff_variant_bits_rt(const Tables &T, const Ctx &c, int ci, int L, int ex)
+{
+    SPL_CHECK(ci >= 0 && ci < 25 && L == combo_len(ci) && ex <= L);
+    const ExSel s = make_exsel(ex);
+    const uint32_t x = T.pext_diff[ci][c.h1], y = T.pext_diff[ci][c.h2], z = T.pext_diff[ci][c.h3];
+    const uint32_t two = (uint32_t)(T.cwr2_pair[L == 2][x & 15u] | T.cwr2_dbl[L == 2][y & 15u]);
+    const uint32_t three = (uint32_t)T.cwr3[(x | y << 3 | z << 6) & 511u];
+    return s.is0 | ((x << 1) & s.m1) | ((two << (7 - L)) & s.m2) | ((three << 10) & s.m3);
+}
+
 // resources_sufficient (:371-394): returns true and the payment if the card is affordable and below the 7-card cap
 __device__ __forceinline__ bool can_buy(const Ctx &c, uint2 cw, uint32_t &pay)
 {
@@ -662,8 +675,8 @@ __device__ __forceinline__ void collect_groups(const Tables &T, const Ctx &c, Fa
     for (int n = 0; n < 5; n++) {
         const int fl = field_of_normal(n);
         const uint32_t inv = T.poly_inv[field(c.gems, 5 * fl) & 15u];
-        Js[n] = (c.A4g >> (5 * fl + 4) & 1u) ? inv : 0u;
-        Jd[n] = (c.A1g >> (5 * fl + 4) & 1u) ? inv : 0u;
+        Js[n] = inv * (c.A4g >> (5 * fl + 4) & 1u);  // a multiply instead of a compare + select: the FMA pipe has room, the ALU pipe has not
+        Jd[n] = inv * (c.A1g >> (5 * fl + 4) & 1u);
     }
     // digit selectors: a group taking L gems returns e_L = max(hold + L - 10, 0) <= 3; collect_same returns e_2
     const uint32_t e1 = (uint32_t)max(c.hold - 9, 0), e2 = (uint32_t)max(c.hold - 8, 0), e3 = (uint32_t)max(c.hold - 7, 0);
@@ -824,7 +837,7 @@ __device__ __forceinline__ void select_family(const Env<P> &e, const Tables &T, 
             const int col = g, e2 = c.hold - 8;
             row = T.ret_same + col * 21;
             base = BASE_SAME + col * 126; nmul = 21;
-            pm = same_variant_bits(T, c, col, e2);
+            pm = same_variant_bits_sel(T, c, col, make_exsel(e2));
             ch.type = T_SAME; ch.slot = col;
             ch.C = 2u << (5 * field_of_normal(col));
         } else {
@@ -832,7 +845,7 @@ __device__ __forceinline__ void select_family(const Env<P> &e, const Tables &T, 
             nmul = L == 1 ? 6 : (L == 2 ? 15 : 20);
             row = T.ret_diff + T.combo_off[ci];
             base = T.combo_base[ci];
-            pm = diff_variant_bits(T, c, ci, L, c.hold + L - 10);
+            pm = diff_variant_bits_rt(T, c, ci, L, c.hold + L - 10);
             ch.type = T_DIFF; ch.slot = ci;
             ch.C = T.combo_c[ci];
         }
