@@ -263,18 +263,18 @@ def other_kernels(pkg, dev, N=262_144, P=2, reps=10):
 
     def timed_after_restore(fn):
         """Kernels that CHANGE the states: every repetition restores the saved mid-game states first (untimed) and brackets
-        only the call itself with its own pair of CUDA events."""
-        total = 0.0
+        only the call itself with its own pair of CUDA events; nothing synchronises inside the loop, so the queue stays
+        full and the pairs measure device time, not the host's launch latency."""
+        pairs = []
         for r in range(reps + 3):
             eng.state.copy_(saved)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
             e1.record()
-            torch.cuda.synchronize(dev)
-            if r >= 3:
-                total += e0.elapsed_time(e1)
-        return total / reps
+            pairs.append((e0, e1))
+        torch.cuda.synchronize(dev)
+        return sum(a.elapsed_time(b) for a, b in pairs[3:]) / reps
 
     W = (8 + 4 * P) * 4
     runs = {

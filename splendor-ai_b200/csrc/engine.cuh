@@ -76,6 +76,9 @@ struct alignas(16) Tables {
     uint32_t recip[68];         // ceil(2^31 / d), d = 1..64 (small_div)
     uint2 buyrow[256];          // card[] for count_legal's affordability test: guard bits already set in the cost (.x | H6),
                                 // and indexed by the raw slot byte (0xFF = empty slot -> filler), so no masking of the id
+    uint4 cardvec[128];         // the observation's 13-byte card vector (vectorize_card, features.py:377-413) as bytes 0..12:
+                                // one-hot over black, blue, green, red, white, yellow | cost black, blue, green, red, white |
+                                // deck_id | points; all zero for the filler entries (an empty slot contributes zeros)
 };
 
 namespace detail {
@@ -230,6 +233,19 @@ __host__ __device__ constexpr Tables make_tables()
         T.poly_inv[h] = x;
     }
     for (int i = 0; i < 256; i++) T.buyrow[i] = uint2{T.card[i & 127].x | H6, T.card[i & 127].y & 31u};  // .y: the colour's bit offset only
+    for (int i = 0; i < 128; i++) T.cardvec[i] = uint4{0u, 0u, 0u, 0u};
+    for (int i = 0; i < SPL_NUM_CARDS; i++) {
+        const detail::CardRow &r = detail::CARD_ROWS[i];
+        const int alpha = r.colour == 0 ? 0 : (r.colour == 1 ? 3 : (r.colour == 2 ? 2 : (r.colour == 3 ? 1 : 4)));  // colour id -> alphabetical rank
+        const uint32_t tier = i < 40 ? 0u : (i < 70 ? 1u : 2u);
+        uint8_t b[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        b[alpha] = 1;
+        b[6] = (uint8_t)r.c[0]; b[7] = (uint8_t)r.c[3]; b[8] = (uint8_t)r.c[2]; b[9] = (uint8_t)r.c[1]; b[10] = (uint8_t)r.c[4];
+        b[11] = (uint8_t)tier; b[12] = (uint8_t)r.points;
+        T.cardvec[i] = uint4{(uint32_t)b[0] | (uint32_t)b[1] << 8 | (uint32_t)b[2] << 16 | (uint32_t)b[3] << 24,
+                             (uint32_t)b[4] | (uint32_t)b[5] << 8 | (uint32_t)b[6] << 16 | (uint32_t)b[7] << 24,
+                             (uint32_t)b[8] | (uint32_t)b[9] << 8 | (uint32_t)b[10] << 16 | (uint32_t)b[11] << 24, (uint32_t)b[12]};
+    }
     for (int d = 1; d <= 64; d++) T.recip[d] = (uint32_t)(((1ull << 31) + (uint64_t)d - 1) / (uint64_t)d);
     return T;
 }
@@ -1352,11 +1368,8 @@ __device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T
         }
         // vectorize_card (features.py:377-413): one-hot over sklearn's alphabetical categories black, blue, green, red,
         // white, yellow (bytes 0..5); the cost in alphabetical order black, blue, green, red, white (6..10); deck_id; points
-        const uint32_t fld = (sh * 13u) >> 6;                       // 0 black 1 red 3 green 4 blue 5 white
-        const uint32_t alpha = (0x412030u >> (4 * fld)) & 15u;      // -> 0 black 1 blue 2 green 3 red 4 white
-        const uint64_t head = present ? ((1ull << (8 * alpha)) | (uint64_t)field(cw.x, 0) << 48 | (uint64_t)field(cw.x, 20) << 56) : 0ull;
-        const uint64_t tail = present ? ((uint64_t)field(cw.x, 15) | (uint64_t)field(cw.x, 5) << 8 | (uint64_t)field(cw.x, 25) << 16 |
-                                         (uint64_t)(cw.y >> 8 & 3u) << 24 | (uint64_t)(cw.y >> 5 & 7u) << 32) : 0ull;
+        const uint4 vec = T.cardvec[id & 127u];  // a table row per card id (the 13 bytes are a pure function of the card)
+        const uint64_t head = (uint64_t)vec.x | (uint64_t)vec.y << 32, tail = (uint64_t)vec.z | (uint64_t)vec.w << 32;
         put_bytes64(o, 70 + 13 * s, head);      // bytes 0..7: one-hot, cost black, cost blue
         put_bytes64(o, 70 + 13 * s + 8, tail);  // bytes 8..12: cost green, red, white, deck_id, points
         done(s == 0 ? 18 : (70 + 13 * s) >> 2, (70 + 13 * (s + 1)) >> 2);  // later cards start at byte 70 + 13 (s + 1)

@@ -13,6 +13,7 @@
 //                       full occupancy; spl_env_step then runs observe_kernel and legal_mask_kernel for the learner's seat.
 //   reset / inject / final_scores: thread-per-env.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -31,11 +32,14 @@ __device__ const uint32_t g_log1p_bits[32] = SPL_LOG1P_BITS;
 
 constexpr int BLOCK = 128;
 
-__device__ __forceinline__ void stage_tables(Tables &sT)
+// Only the observation kernel reads the card-vector table at the end of Tables: every other kernel stages the part before it.
+constexpr int TABLES_RULE_BYTES = (int)offsetof(Tables, cardvec);
+static_assert(TABLES_RULE_BYTES % 16 == 0, "the rule tables must end on a 16-byte boundary");
+__device__ __forceinline__ void stage_tables(Tables &sT, int bytes = TABLES_RULE_BYTES)
 {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(&g_tables);
     uint32_t *dst = reinterpret_cast<uint32_t *>(&sT);
-    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < bytes / 4; i += blockDim.x) dst[i] = src[i];
     __syncthreads();
 }
 static_assert(sizeof(Tables) % 4 == 0, "Tables must be word-copyable");
@@ -48,7 +52,7 @@ __device__ __forceinline__ void stage_tables_nosync(Tables &sT)
     const uint4 *src = reinterpret_cast<const uint4 *>(&g_tables);
     uint4 *dst = reinterpret_cast<uint4 *>(&sT);
 #pragma unroll 4
-    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 16); i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < TABLES_RULE_BYTES / 16; i += blockDim.x) dst[i] = src[i];
 }
 constexpr int ENV_TB = 256;        // threads per block of the persistent thread-per-env kernels (step, env move)
 constexpr int STEP_BLOCKS_PER_SM = 4, ENV_MOVE_BLOCKS_PER_SM = 3;  // what the register counts (64 / 80) let reside
@@ -654,7 +658,7 @@ template <int P>
 __global__ void __launch_bounds__(TILE_TB_MAX) observe_kernel(const uint4 *state, const int8_t *seat, float *obs, int64_t N)
 {
     __shared__ Tables sT;
-    stage_tables(sT);
+    stage_tables(sT, (int)sizeof(Tables));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *wtile = dyn_tile + warp * (32 * OBS_WORDS);  // this warp's 32 byte rows
     for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32; base < N; base += (int64_t)gridDim.x * blockDim.x) {
@@ -924,10 +928,9 @@ static int resident_blocks(size_t dyn_bytes)  // per SM, by shared memory (227 K
     default: return SPL_E_BADARG;      \
     }
 
-template <int P, int MODE>
-static int launch_pool(const PlayoutArgs &a, cudaStream_t stream)
+template <int P, int MODE, int NW>
+static int launch_pool_nw(const PlayoutArgs &a, cudaStream_t stream)
 {
-    constexpr int NW = SPL_POOL_WARPS;
     using Sm = PoolSmem<P, NW>;
     auto kernel = playout_pool_kernel<P, MODE, NW>;
     static bool configured[SPL_MAX_DEVICES] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
@@ -942,6 +945,17 @@ static int launch_pool(const PlayoutArgs &a, cudaStream_t stream)
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     kernel<<<grid, 32 * NW, sizeof(Sm), stream>>>(a);
     return SPL_OK;
+}
+// Two pool sizes: 20 warps per block (19 stepping) for launches that keep the pools refilled, and 19 warps (104 instead
+// of 96 registers per thread: no spills, a slightly shorter step) for launches whose games all fit the pools at once, where
+// the time is set by the latency of the rounds, not by the issue rate (65,536 games: 0.3917 -> 0.3866 ms; 2^20 games:
+// 2.076 -> 2.072e10 the other way, profiles/r2_playout.md).
+template <int P, int MODE>
+static int launch_pool(const PlayoutArgs &a, cudaStream_t stream)
+{
+    constexpr int NW = SPL_POOL_WARPS;
+    if (a.n_games <= (int64_t)sm_count() * SPL_POOL_BLOCKS_PER_SM * 32 * (NW - 2)) return launch_pool_nw<P, MODE, NW - 1>(a, stream);
+    return launch_pool_nw<P, MODE, NW>(a, stream);
 }
 
 extern "C" {

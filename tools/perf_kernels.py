@@ -56,18 +56,18 @@ for N in a.envs:
     res["observe"] = (timed(lambda: eng.observe(out=obs_buf), a.reps), W + 1060)
 
     def timed_after_restore(fn, reps):
-        """state-changing kernels: restore the saved states (untimed) before every repetition, one event pair per call"""
-        total = 0.0
+        """state-changing kernels: restore the saved states (untimed) before every repetition, one event pair per call, no
+        synchronisation inside the loop (the pairs then measure device time, not the host's launch latency)"""
+        pairs = []
         for r in range(reps + 3):
             eng.state.copy_(saved)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
             e1.record()
-            torch.cuda.synchronize()
-            if r >= 3:
-                total += e0.elapsed_time(e1)
-        return total / reps
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in pairs[3:]) / reps
 
     res["step"] = (timed_after_restore(lambda: eng.step(act), a.reps), 2 * W + 2 + 3)
     res["env_step"] = (timed_after_restore(lambda: eng.env_step(learner, act), a.reps), 2 * W + 440 + 1060 + 3 + 3)
