@@ -591,30 +591,12 @@ __device__ __forceinline__ int reserve_variants(const Ctx &c)
 }
 __device__ __forceinline__ int combo_len(int ci) { return ci < 5 ? 1 : (ci < 15 ? 2 : 3); }
 
-// Bitmask (bit v = variant v) of the return variants of collect_diff combination ci that the agent can pay when it must
-// return `ex` gems (<= 0: only "return nothing").  Table lookups only: pext of the held-colour masks onto the combo's
-// other colours, then the combinations_with_replacement patterns (actions.py:188-199).
-__device__ __forceinline__ uint32_t diff_variant_bits(const Tables &T, const Ctx &c, int ci, int L, int ex)
-{
-    SPL_CHECK(ci >= 0 && ci < 25 && c.h1 < 64 && c.h2 < 64 && c.h3 < 64 && L == combo_len(ci));
-    const uint32_t x = T.pext_diff[ci][c.h1], y = T.pext_diff[ci][c.h2], z = T.pext_diff[ci][c.h3];
-    const int kk = 6 - L;
-    const uint32_t two = L == 1 ? 0u : (uint32_t)(T.cwr2_pair[L == 2][x & 15u] | T.cwr2_dbl[L == 2][y & 15u]);
-    const uint32_t three = L == 3 ? (uint32_t)T.cwr3[x | y << 3 | z << 6] : 0u;
-    return ex <= 0 ? 1u : (ex == 1 ? x << 1 : (ex == 2 ? two << (1 + kk) : three << 10));
-}
-// Same for collect_same colour `col` (actions.py:145-174): none | pairs 1..10 | one of 11..15 | two of 16..20
-__device__ __forceinline__ uint32_t same_variant_bits(const Tables &T, const Ctx &c, int col, int e2)
-{
-    SPL_CHECK(col >= 0 && col < 5 && c.h1 < 64 && c.h2 < 64);
-    const uint32_t x = T.pext_same[col][c.h1], y = T.pext_same[col][c.h2];
-    return e2 <= 0 ? 1u : (e2 == 1 ? x << 11 : ((uint32_t)T.pairs5[x] << 1 | y << 16));
-}
-
-// The same two functions for a caller that evaluates MANY groups of one env (the mask row builder): the case "how many gems
-// must go back" is the same for all groups of a size, so it is turned into AND-masks once and every group becomes a short
-// branch-free sequence (lookups + shifts + AND/OR).  With the nested selects above the compiler emitted a branch region per
-// group, executed at ~9 active lanes: 41 % of the mask kernel's instructions (profiles/r2_kernels.md).
+// Bitmask (bit v = variant v) of the return variants of a collect group that the agent can pay when it must return `ex`
+// gems (<= 0: only "return nothing").  Table lookups only: pext of the held-colour masks onto the group's other colours, then
+// the combinations_with_replacement patterns (actions.py:145-199).  collect_same colour: none | pairs 1..10 | one of 11..15 |
+// two of 16..20.  Callers never branch on the case "how many gems must go back": it is turned into AND-masks (ExSel) and
+// every group becomes a short branch-free sequence of lookups, shifts and AND/OR.  (A first form with nested selects
+// compiled to one branch region per group, executed at ~9 active lanes: 41 % of the mask kernel's instructions.)
 struct ExSel { uint32_t is0, m1, m2, m3; };  // excess <= 0 -> bit 0 ("return nothing") ; == 1 / 2 / 3 -> all-ones masks
 __device__ __forceinline__ ExSel make_exsel(int ex)
 {

@@ -56,18 +56,30 @@ for N in a.envs:
     res["observe"] = (timed(lambda: eng.observe(out=obs_buf), a.reps), W + 1060)
 
     def timed_after_restore(fn, reps):
-        """state-changing kernels: restore the saved states (untimed) before every repetition, one event pair per call, no
-        synchronisation inside the loop (the pairs then measure device time, not the host's launch latency)"""
-        pairs = []
-        for r in range(reps + 3):
-            eng.state.copy_(saved)
+        """state-changing kernels: {restore the saved states; call} captured in a CUDA graph and replayed back to back, minus
+        the restore-only graph (launch by launch from Python the host is slower than a 16 us kernel)"""
+        def graph_ms(body):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                body()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            for _ in range(reps):
+                g.replay()
             e1.record()
-            pairs.append((e0, e1))
-        torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in pairs[3:]) / reps
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        return graph_ms(lambda: (eng.state.copy_(saved), fn())) - graph_ms(lambda: eng.state.copy_(saved))
 
     res["step"] = (timed_after_restore(lambda: eng.step(act), a.reps), 2 * W + 2 + 3)
     res["env_step"] = (timed_after_restore(lambda: eng.env_step(learner, act), a.reps), 2 * W + 440 + 1060 + 3 + 3)
