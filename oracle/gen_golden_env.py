@@ -120,7 +120,8 @@ def learner_choice(policy, rng, idxs, t):
     return int(rng.choice(idxs))
 
 
-def record_episode(P, seat, seed, game, policy, opponents, shuffle_turns, max_calls=400, pad=0):
+def record_episode(P, seat, seed, game, policy, opponents, shuffle_turns, max_calls=400, pad=0, np_seed=None):
+    """seat=None: the env draws the learner's seat itself (fixed_turn=None -> np.random.randint, splendor_env.py:107-111)."""
     lists, nobles = O.synth_game(seed, game, P)
     log = []
     if opponents == "philox":
@@ -142,9 +143,13 @@ def record_episode(P, seat, seed, game, policy, opponents, shuffle_turns, max_ca
         ep["legal"].append(np.nonzero(mask)[0].astype(np.uint16))
         ep["snap"].append(snapshot(env.game_rule))
 
+    if np_seed is not None:
+        np.random.seed(np_seed)
     with injected_decks(lists, nobles):
         obs, info = env.reset()
-    assert info["my_id"] == seat
+    if seat is None:
+        seat = ep["my_id"] = int(info["my_id"])
+    assert info["my_id"] == seat == env.my_turn
     if pad:
         # Harness edit of the reference's STATE (not its code): every agent's action trace gets `pad` placeholder entries
         # right after reset, as if `pad` full rounds had been played without changing anything else.  Only the trace
@@ -190,6 +195,7 @@ PLAN = [
     ("env_3p", 3, 32, 200, 3, ("random", "greedy", "random"), "philox"),
     ("env_4p", 4, 33, 300, 2, ("random", "greedy"), "philox"),
     ("env_cap", None, 34, 400, 1, ("scripted",), "scripted"),  # 100-round cap: 2, 3 and 4 players, learner seat 0 / 1 / 3
+    ("env_rand", -3, 35, 500, 6, ("random", "greedy"), "philox"),  # 3 players, the env draws the learner's seat and shuffles the opponents
 ]
 
 if __name__ == "__main__":
@@ -199,7 +205,11 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         t0, eps, game = time.time(), [], first
-        if P is None:
+        if P is not None and P < 0:
+            for k in range(per_seat):
+                eps.append(record_episode(-P, None, seed, game, policies[k % len(policies)], opponents, shuffle_turns=True, np_seed=7000 + k))
+                game += 1
+        elif P is None:
             # scripted hoarders on every seat.  2 players: a game that ends by score (id 400) and one that runs into the
             # 100-round cap on its own (id 401; found with the oracle).  3 and 4 players: turn counters preset to 95 (pad).
             for PP, seat, g, pad in ((2, 0, 400, 0), (2, 1, 401, 0), (2, 0, 402, 0), (3, 1, 403, 95), (4, 3, 404, 95), (4, 0, 405, 95)):

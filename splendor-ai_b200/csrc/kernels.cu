@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(32 * NW, SPL_POOL_BLOCKS_PER_SM) playout_pool_
                 survive = true;
                 if (!keeper) {
                     const uint64_t game = (MODE == POOL_STATES && a.game_ids) ? a.game_ids[gid] : a.first_game + gid;
-                    const DeckSrc src{(MODE != POOL_FRESH && a.decks) ? a.decks + (int64_t)gid * SPL_DECK_BYTES : nullptr, a.seed, game, a.rk};
+                    const DeckSrc src{(MODE != POOL_FRESH && a.decks) ? a.decks + (int64_t)gid * SPL_DECK_BYTES : nullptr, a.seed, game, a.rk, &T};
                     t = (int)turns_total(e);
                     const int t_end = (int)t0 + a.max_steps;
                     if (MODE == POOL_STATES) kind = game_ends(e, a.flags);  // a game that was over when it was handed in

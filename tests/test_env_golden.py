@@ -26,7 +26,7 @@ def opponents_until_learner(oracle, s, ep, log=None):
         oracle.step(s, a)
 
 
-@pytest.mark.parametrize("name", ["env_2p", "env_3p", "env_4p", "env_cap"])
+@pytest.mark.parametrize("name", ["env_2p", "env_3p", "env_4p", "env_cap", "env_rand"])
 def test_oracle_env_emulation_matches_reference_env(oracle, name):
     eps = load_env_episodes(name)
     calls = 0

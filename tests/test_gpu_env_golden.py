@@ -37,7 +37,7 @@ def nobles5(eps):
     return np.stack([np.concatenate([e["nobles"], [255] * (5 - len(e["nobles"]))]) for e in eps]).astype(np.uint8)
 
 
-@pytest.mark.parametrize("name", ["env_2p", "env_3p", "env_4p"])
+@pytest.mark.parametrize("name", ["env_2p", "env_3p", "env_4p", "env_rand"])
 def test_spl_env_step_replays_reference_env(pkg, name):
     """spl_env_step with injected deck orders (explicit-list decks) and per-env game ids: learner move, in-kernel
     Philox opponents, learner's mask + observation - against what the reference env returned."""
@@ -225,3 +225,24 @@ def test_policy_opponents_match_oracle_emulation(pkg, oracle):
                 done[e] = True
                 finished += 1
     assert finished >= N // 2
+
+
+def test_vec_env_raises_before_it_changes_anything(pkg):
+    """raise_on_illegal=True: the reference raises ValueError before it mutates (splendor_env.py:139-153); the vector env
+    tests the action bits of its current masks first, so a caught error leaves states, masks and bookkeeping untouched."""
+    N = 64
+    venv = pkg.SplendorVecEnv(N, 2, seed=5, raise_on_illegal=True)
+    obs, info = venv.reset()
+    before = venv.state.clone()
+    mask = info["legal_mask"].clone()
+    legal = [int(unpack_mask(m)[0]) for m in mask.cpu().numpy()]
+    bad = torch.tensor(legal, dtype=torch.int16)
+    bad[17] = 3509 if 3509 not in unpack_mask(mask[17].cpu().numpy()).tolist() else 0
+    with pytest.raises(ValueError):
+        venv.step(bad)
+    assert torch.equal(venv.state, before) and torch.equal(venv.legal_mask, mask) and not bool(venv._done.any())
+    with pytest.raises(ValueError):
+        venv.step(torch.full((N,), 3510, dtype=torch.int16))
+    assert torch.equal(venv.state, before)
+    obs2, reward, term, trunc, info2 = venv.step(torch.tensor(legal, dtype=torch.int16))  # and it still works afterwards
+    assert not bool(info2["illegal"].any())
