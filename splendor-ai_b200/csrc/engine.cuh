@@ -52,10 +52,13 @@ enum ActType { T_PASS = 0, T_RESERVE = 1, T_SAME = 2, T_DIFF = 3, T_BUY_RESERVE 
 constexpr int BASE_RESERVE = 6, BASE_SAME = 510, BASE_DIFF = 1140, BASE_BUY_RESERVE = 3420, BASE_BUY_AVAILABLE = 3438;
 
 struct alignas(16) Tables {
+    // Four parts, each starting on a 16-byte boundary, ordered so that a kernel stages only a PREFIX (plus, for the observation
+    // kernel, the last part): [card, noble] everyone | decode / apply (step) | legality patterns (mask) | counting and
+    // selecting (playouts, expansion) | observation card vectors.  kernels.cu: TABLES_*_BYTES.
     uint2 card[128];         // .x = cost (g6, yellow field 0) ; .y = 5*colour_field | points << 5 | tier << 8;
                              // entries 90..127 (an empty slot's 0xFF & 127 lands on 127): colour shift = yellow, never buyable
     uint32_t noble[16];      // requirement (g6); entry 15 = "no noble" (unsatisfiable)
-    uint32_t combo_c[25];    // collect_diff combo ci: collected gems (g6).  ci 0..4 L=1, 5..14 L=2, 15..24 L=3
+    alignas(16) uint32_t combo_c[25];  // collect_diff combo ci: collected gems (g6).  ci 0..4 L=1, 5..14 L=2, 15..24 L=3
     uint16_t combo_base[25]; // ALL_ACTIONS index of (combo ci, noble slot 0, variant 0)
     uint16_t combo_off[25];  // first entry of the combo's variants in ret_diff
     uint8_t combo_mask[25];  // 6-bit field mask of the combo's colours
@@ -63,7 +66,7 @@ struct alignas(16) Tables {
     uint32_t ret_diff[380];  // returned gems (g6) of variant v: 6 / 15 / 20 variants per combo of length 1 / 2 / 3
     uint32_t ret_same[105];  // [c*21 + v], c = NORMAL_COLORS index
     // feasibility LUTs: which return variants of a group the agent can pay, from its held-colour masks (no scanning)
-    uint8_t pext_diff[25][64];  // 6-bit colour-field mask -> bits over the combo's OTHER colours, in variant order
+    alignas(16) uint8_t pext_diff[25][64];  // 6-bit colour-field mask -> bits over the combo's OTHER colours, in variant order
     uint8_t pext_same[5][64];   // same for collect_same colour c (5 other colours)
     uint16_t pairs5[32];        // held>=1 bits over 5 others -> combinations(others, 2) bits (collect_same variants 1..10)
     uint16_t cwr2_pair[2][16];  // [k==4][x]: k others held>=1 -> bits of the i<j entries of combinations_with_replacement(k,2)
@@ -71,7 +74,7 @@ struct alignas(16) Tables {
     uint16_t cwr3[512];         // k=3: x | y<<3 | z<<6 (held >=1/>=2/>=3) -> bits of combinations_with_replacement(3,3)
     // return-multiset generating functions (see collect_groups below): (1 + x + .. + x^lvl)^n and 1 / (1 + x + .. + x^lvl)
     // as base-256 digit strings modulo 2^32
-    uint32_t poly_pow[3][8];    // [lvl-1][n], n = 0..6
+    alignas(16) uint32_t poly_pow[3][8];  // [lvl-1][n], n = 0..6
     uint32_t poly_inv[16];      // [gems held of the colour] (level = min(held, 3))
     uint32_t recip[68];         // ceil(2^31 / d), d = 1..64 (small_div)
     uint2 buyrow[256];          // card[] for count_legal's affordability test: guard bits already set in the cost (.x | H6),
@@ -926,8 +929,10 @@ __device__ __forceinline__ void select_legal(const Env<P> &e, const Tables &T, c
 
 // Is ALL_ACTIONS[idx] legal for the seat to move?  Decodes it into ch either way (build_action, gym/envs/utils.py:43-145).
 // This is the membership form of the same rules, written independently of count/select so the two cross-check.
+// Tcount: the tables the (rare) pass check counts the legal actions with - a kernel that stages only the decode / apply
+// part of the tables into shared memory passes the complete copy in global memory here.
 template <int P>
-__device__ __forceinline__ bool decode_and_check(const Env<P> &e, const Tables &T, const Ctx &c, int idx, Choice &ch)
+__device__ __forceinline__ bool decode_and_check(const Env<P> &e, const Tables &T, const Ctx &c, int idx, Choice &ch, const Tables &Tcount)
 {
     ch.idx = idx; ch.C = 0; ch.R = 0; ch.info = 0; ch.slot = 0; ch.n = 0; ch.type = T_PASS;
     if (idx < 0 || idx >= SPL_NUM_ACTIONS) return false;
@@ -936,7 +941,7 @@ __device__ __forceinline__ bool decode_and_check(const Env<P> &e, const Tables &
     if (idx < BASE_RESERVE) {
         FamilyCounts f;
         ch.n = idx;
-        ok = count_legal(e, T, c, f) == 0;
+        ok = count_legal(e, Tcount, c, f) == 0;
     } else if (idx < BASE_SAME) {
         const int r = idx - BASE_RESERVE, p = r / 42, v = r % 7;
         ch.type = T_RESERVE; ch.slot = p; ch.n = (r % 42) / 7;
@@ -985,6 +990,12 @@ __device__ __forceinline__ bool decode_and_check(const Env<P> &e, const Tables &
     }
     const bool noble_ok = S ? (ch.n >= 1 && (S >> (ch.n - 1) & 1)) : ch.n == 0;
     return ok && noble_ok;
+}
+
+template <int P>
+__device__ __forceinline__ bool decode_and_check(const Env<P> &e, const Tables &T, const Ctx &c, int idx, Choice &ch)
+{
+    return decode_and_check(e, T, c, idx, ch, T);
 }
 
 // ------------------------------------------------------------------------------------------------ successor
@@ -1346,8 +1357,9 @@ __device__ __forceinline__ void put_bytes64(uint32_t *o, int idx, uint64_t pat) 
 }
 
 // `done(w0, w1)` is called when words [w0, w1) are final: the card vectors as each card is finished, the metrics last
-template <int P, class Done = MaskKeep>
-__device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const Tables &T, int seat, uint32_t *o, Done done = Done())
+// (TT: Tables, or any struct with its card / noble / cardvec members - the observation kernel stages only those)
+template <int P, class Done = MaskKeep, class TT = Tables>
+__device__ __forceinline__ void thread_fill_obs(const Env<P> &e, const TT &T, int seat, uint32_t *o, Done done = Done())
 {
     uint32_t gems = e.pg[0], cards = e.pc[0], resv = e.pr[0], pinfo = e.pi[0];
 #pragma unroll

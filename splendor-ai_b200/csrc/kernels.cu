@@ -35,27 +35,29 @@ __device__ const uint32_t g_log1p_bits[32] = SPL_LOG1P_BITS;
 
 constexpr int BLOCK = 128;
 
-// Only the observation kernel reads the card-vector table at the end of Tables: every other kernel stages the part before it.
-constexpr int TABLES_RULE_BYTES = (int)offsetof(Tables, cardvec);
-static_assert(TABLES_RULE_BYTES % 16 == 0, "the rule tables must end on a 16-byte boundary");
-__device__ __forceinline__ void stage_tables(Tables &sT, int bytes = TABLES_RULE_BYTES)
+// A kernel stages only the part of Tables it reads (engine.cuh: the struct is ordered for this).  Every boundary is a multiple
+// of 16 bytes: the copies are 16-byte loads from L2 and 16-byte shared-memory stores.
+constexpr int TABLES_HEAD_BYTES = (int)offsetof(Tables, combo_c);    // card + noble: the observation kernel (with cardvec)
+constexpr int TABLES_STEP_BYTES = (int)offsetof(Tables, pext_diff);  // + action decode / apply: step
+constexpr int TABLES_MASK_BYTES = (int)offsetof(Tables, poly_pow);   // + legality patterns: legal mask
+constexpr int TABLES_RULE_BYTES = (int)offsetof(Tables, cardvec);    // + counting / selecting: playouts, env move, expansion
+static_assert(TABLES_HEAD_BYTES % 16 == 0 && TABLES_STEP_BYTES % 16 == 0 && TABLES_MASK_BYTES % 16 == 0 && TABLES_RULE_BYTES % 16 == 0 &&
+                  sizeof(Tables) % 16 == 0 && alignof(Tables) >= 16,
+              "the parts of Tables must be copyable in 16-byte pieces");
+// bytes [begin, end) of the tables -> the block's copy, WITHOUT a barrier: a caller issues its first env's loads, calls
+// this (every thread has a few independent 16-byte loads in flight), then synchronises - the table copy and the state
+// loads overlap instead of forming a serial prologue.
+__device__ __forceinline__ void stage_tables_nosync(Tables &sT, int begin = 0, int end = TABLES_RULE_BYTES)
 {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(&g_tables);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&sT);
-    for (int i = threadIdx.x; i < bytes / 4; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-}
-static_assert(sizeof(Tables) % 4 == 0, "Tables must be word-copyable");
-// The same copy for the persistent thread-per-env kernels, WITHOUT the barrier: the caller issues its first env's loads,
-// calls this (every thread has a few independent 16-byte loads in flight), then synchronises - the table copy and the
-// state loads overlap instead of forming a serial prologue.
-__device__ __forceinline__ void stage_tables_nosync(Tables &sT)
-{
-    static_assert(sizeof(Tables) % 16 == 0 && alignof(Tables) >= 16, "Tables must be copyable in 16-byte pieces");
     const uint4 *src = reinterpret_cast<const uint4 *>(&g_tables);
     uint4 *dst = reinterpret_cast<uint4 *>(&sT);
 #pragma unroll 4
-    for (int i = threadIdx.x; i < TABLES_RULE_BYTES / 16; i += blockDim.x) dst[i] = src[i];
+    for (int i = begin / 16 + threadIdx.x; i < end / 16; i += blockDim.x) dst[i] = src[i];
+}
+__device__ __forceinline__ void stage_tables(Tables &sT, int bytes = TABLES_RULE_BYTES)
+{
+    stage_tables_nosync(sT, 0, bytes);
+    __syncthreads();
 }
 constexpr int ENV_TB = 256;        // threads per block of the persistent thread-per-env kernels (step, env move)
 constexpr int STEP_BLOCKS_PER_SM = 4, ENV_MOVE_BLOCKS_PER_SM = 3;  // what the register counts (64 / 80) let reside
@@ -342,7 +344,8 @@ __global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_
                                                       const uint64_t *game_ids, const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal,
                                                       int64_t N, uint32_t flags)
 {
-    __shared__ __align__(16) Tables sT;  // (reading the tables through L1 instead of staging them: no difference, A/B r2r)
+    __shared__ __align__(16) unsigned char sT_bytes[TABLES_STEP_BYTES];  // the part of Tables that decode + apply read
+    Tables &sT = *reinterpret_cast<Tables *>(sT_bytes);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Env<P> e;
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_
         a = action[i];
         load_env(e, state, N, i);
     }
-    stage_tables_nosync(sT);
+    stage_tables_nosync(sT, 0, TABLES_STEP_BYTES);  // decode + apply read a quarter of the tables
     __syncthreads();
     // (prefetching the next env's state across the loop was measured slower: 103 registers, 0.0167 -> 0.0211 ms per 262,144 envs)
     while (i < N) {
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_
             Ctx c;
             Choice ch;
             make_ctx(e, sT, c);
-            if (decode_and_check(e, sT, c, a, ch)) {
+            if (decode_and_check(e, sT, c, a, ch, g_tables)) {  // (a pass is checked against the complete tables in global memory)
                 const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
                 rew = apply_action(e, ch, src);
             } else {
@@ -587,63 +590,107 @@ __device__ __forceinline__ void mask_tile_store(const uint32_t *wtile, uint32_t 
     }
 }
 
-// a warp's staged byte rows [0, n) -> float32 observations: lane l writes entries l, l + 32, ... of each row (coalesced
-// 128-byte stores); bytes widen to float with the 2^23 trick (one OR, one FADD, exact below 2^23)
+// Observation rows are staged as BYTES, DENSE: row j of a warp's tile starts at byte 265 j, so the 32 rows are one flat
+// 8,480-byte array whose float32 image is one flat, 16-byte aligned 33,920-byte span of the output.  The warp widens it four
+// entries per lane and step: one 32-bit shared-memory load, four byte permutes that drop each byte into 0x4B0000bb (the
+// 2^23 trick: 8388608 + b as a float, exact), four FADD, one 128-bit store - 2.5 instructions per entry instead of 4 with
+// scalar stores (the row-by-row loop was 37 % of the kernel's instructions and throttled the load/store pipe).
+constexpr int OBS_TILE_BYTES = 32 * SPL_OBS_SIZE;
+static_assert(OBS_TILE_BYTES % 16 == 0, "a warp's observation rows must be a 16-byte multiple");
 __device__ __forceinline__ float byte_to_float(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
-__device__ __forceinline__ void obs_tile_store(const uint8_t *wtile, float *out, int n, int lane)
+__device__ __forceinline__ float byte_of_word_to_float(uint32_t w, int j) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u + j)) - 8388608.0f; }
+__device__ __forceinline__ void obs_tile_store(const uint32_t *wtile, float *out, int n, int lane)
 {
-    constexpr int FULL = SPL_OBS_SIZE / 32;  // 8 full 32-entry groups, then 9 entries
-#pragma unroll 2
-    for (int j = 0; j < n; j++) {
-        const uint8_t *row = wtile + j * OBS_ROW_BYTES;
-        float *dst = out + (int64_t)j * SPL_OBS_SIZE;
+    const int total = n * SPL_OBS_SIZE;
+    if (((uintptr_t)out & 15u) == 0) {
+        const int nq = total >> 2;
+        float4 *out4 = reinterpret_cast<float4 *>(out);
+        // eight quads per lane in flight: the loads of a batch are issued together, and a batch's eight 128-bit stores use
+        // distinct registers (a store holds its source registers until the load/store unit has read them)
+        constexpr int BATCH = 8;
+        int q = lane;
+        for (; q + 32 * (BATCH - 1) < nq; q += 32 * BATCH) {
+            uint32_t w[BATCH];
 #pragma unroll
-        for (int k = 0; k < FULL; k++) dst[lane + 32 * k] = byte_to_float(row[lane + 32 * k]);  // (the 7 special entries: obs_patch_special)
-        if (lane < SPL_OBS_SIZE - 32 * FULL) dst[lane + 32 * FULL] = byte_to_float(row[lane + 32 * FULL]);
+            for (int u = 0; u < BATCH; u++) w[u] = wtile[q + 32 * u];
+#pragma unroll
+            for (int u = 0; u < BATCH; u++)
+                out4[q + 32 * u] = make_float4(byte_of_word_to_float(w[u], 0), byte_of_word_to_float(w[u], 1), byte_of_word_to_float(w[u], 2),
+                                               byte_of_word_to_float(w[u], 3));
+        }
+        for (; q < nq; q += 32) {
+            const uint32_t w = wtile[q];
+            out4[q] = make_float4(byte_of_word_to_float(w, 0), byte_of_word_to_float(w, 1), byte_of_word_to_float(w, 2), byte_of_word_to_float(w, 3));
+        }
+        const int f = (nq << 2) + lane;  // a ragged last tile: up to three entries left
+        if (f < total) out[f] = byte_to_float(reinterpret_cast<const uint8_t *>(wtile)[f]);
+    } else {  // a caller's buffer that is only float-aligned
+        for (int f = lane; f < total; f += 32) out[f] = byte_to_float(reinterpret_cast<const uint8_t *>(wtile)[f]);
     }
 }
-// The seven entries of a row that are not plain bytes - turns [1], the variance [6] (one IEEE division), log(1 + buying
-// power) [19..23] - are written by the lane that OWNS the row, all 32 lanes at once, after the warp's plain stores.  Round 1
-// decoded them inside the row loop: the division's slow path ran once per ROW at one active lane (12 % of the kernel's
-// instructions, 24 % with the other two cases; profiles/r2_kernels.md).
-__device__ __forceinline__ void obs_patch_special(const uint8_t *row, float *dst)
-{
-    dst[1] = obs_entry(row, 1, g_log1p_bits);
-    dst[6] = obs_entry(row, 6, g_log1p_bits);
-#pragma unroll
-    for (int w = 19; w < 24; w++) dst[w] = obs_entry(row, w, g_log1p_bits);
-}
-struct ObsRowSink {
-    uint32_t *row;
+// A lane's row starts (lane & 3) bytes into a word: its finished staged words go out shifted by that much.  Word k of the
+// row's span holds the top of o[k - 1] and the bottom of o[k]; k = 0 (shared with the previous lane's last bytes) and
+// k = 66 are written by the kernel after the row is complete.  thread_fill_obs finishes the card words [18, 66) in
+// ascending ranges, then [0, 18), then the spill words [66, 69) - so a range's first word can use the word before it,
+// except at 18 (word 17 is final only with [0, 18)).
+struct ObsDenseSink {
+    uint32_t *dst;  // the tile word that holds this row's byte 0
     const uint32_t *o;
+    uint32_t sh;    // 8 * (lane & 3)
     __device__ __forceinline__ void operator()(int w0, int w1) const
     {
+        const int k0 = (w0 == 0 || w0 == 18) ? w0 + 1 : w0, k1 = w1 == 18 ? 19 : (w1 < 66 ? w1 : 66);
 #pragma unroll
-        for (int w = w0; w < w1; w++) row[w] = o[w];
+        for (int k = k0; k < k1; k++) dst[k] = __funnelshift_l(o[k - 1], o[k], sh);
     }
 };
+// what thread_fill_obs reads of the tables: 3 KB instead of 13 (card and noble are the head of Tables)
+struct alignas(16) ObsTables {
+    uint2 card[128];
+    uint32_t noble[16];
+    uint4 cardvec[128];
+};
+static_assert(offsetof(ObsTables, cardvec) == TABLES_HEAD_BYTES && offsetof(Tables, noble) == offsetof(ObsTables, noble), "ObsTables mirrors the head of Tables");
 
-constexpr int MASK_TB = 224;     // default block sizes (warps work independently in the mask kernel; the tile caps residency)
-constexpr int OBS_TB = 128;
-constexpr int TILE_TB_MAX = 512; // SPL_MASK_BLOCK / SPL_OBS_BLOCK may raise the block size up to this
+constexpr int TILE_TB_MAX = 512;  // the row kernels' largest block (row_shape picks warps per block and blocks per SM)
 
+// Software-pipelined over the warp's tiles: the NEXT tile's states (and seats) are loaded into registers before the current
+// one is built - the tile, not the register file, caps residency here (70 of 146 registers used at 14 warps per SM), and
+// waiting for the state loads was 17 % of all stall samples (profiles/r2_kernels.md, r3g).  The first loads are issued
+// before the table copy; the wait for the previous bulk store comes after the context is built, just before the first
+// write to the tile.
 template <int P>
 __global__ void __launch_bounds__(TILE_TB_MAX) legal_mask_kernel(const uint4 *state, const int8_t *seat, uint32_t *mask, int64_t N)
 {
-    __shared__ Tables sT;
-    stage_tables(sT);
+    __shared__ __align__(16) unsigned char sT_bytes[TABLES_MASK_BYTES];  // the part of Tables the row builder reads
+    Tables &sT = *reinterpret_cast<Tables *>(sT_bytes);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    Env<P> nxt;
+    int nseat = 0;
+    if (base + lane < N) {
+        load_env(nxt, state, N, base + lane);
+        if (seat) nseat = seat[base + lane];
+    }
+    stage_tables(sT, TABLES_MASK_BYTES);
     uint32_t *wtile = dyn_tile + warp * (32 * SPL_MASK_WORDS);  // this warp's 32 dense rows
-    for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32; base < N; base += (int64_t)gridDim.x * blockDim.x) {
+    for (; base < N; base += stride) {
         const int64_t i = base + lane;
+        Env<P> e = nxt;
+        const int eseat = nseat;
+        if (i + stride < N) {
+            load_env(nxt, state, N, i + stride);
+            if (seat) nseat = seat[i + stride];
+        }
+        Ctx c;
+        if (i < N) {
+            if (seat) e.meta = (e.meta & ~(3u << 20)) | ((uint32_t)eseat << 20);  // the mask of this seat, whoever is to move
+            make_ctx(e, sT, c);
+        }
         if (lane == 0) bulk_store_wait_read();  // the previous tile has left shared memory
         __syncwarp();
         if (i < N) {
-            Env<P> e;
-            load_env(e, state, N, i);
-            if (seat) e.meta = (e.meta & ~(3u << 20)) | ((uint32_t)seat[i] << 20);  // the mask of this seat, whoever is to move
-            Ctx c;
-            make_ctx(e, sT, c);
             uint32_t m[MASK_REGS];
 #pragma unroll
             for (int w = 0; w < MASK_REGS; w++) m[w] = 0;
@@ -657,27 +704,66 @@ __global__ void __launch_bounds__(TILE_TB_MAX) legal_mask_kernel(const uint4 *st
     if (lane == 0) bulk_store_wait_read();
 }
 
+// The seven entries of a row that are not plain bytes - turns [1], the variance [6] (one IEEE division), log(1 + buying
+// power) [19..23] - are written by the lane that OWNS the row from its registers, all 32 lanes at once, after the warp's
+// plain stores.  Round 1 decoded them inside the row loop: the division's slow path ran once per ROW at one active lane
+// (12 % of the kernel's instructions, 24 % with the other two cases; profiles/r2_kernels.md).
 template <int P>
 __global__ void __launch_bounds__(TILE_TB_MAX) observe_kernel(const uint4 *state, const int8_t *seat, float *obs, int64_t N)
 {
-    __shared__ Tables sT;
-    stage_tables(sT, (int)sizeof(Tables));
+    __shared__ ObsTables sT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *wtile = dyn_tile + warp * (32 * OBS_WORDS);  // this warp's 32 byte rows
-    for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32; base < N; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    Env<P> nxt;  // software-pipelined like the mask kernel: the next tile's states are in flight while this one is built
+    int nseat = -1;
+    if (base + lane < N) {
+        load_env(nxt, state, N, base + lane);
+        if (seat) nseat = seat[base + lane];
+    }
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&g_tables), *vec = g_tables.cardvec;
+        uint4 *dst = reinterpret_cast<uint4 *>(&sT);
+        for (int i = threadIdx.x; i < TABLES_HEAD_BYTES / 16; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < 128; i += blockDim.x) sT.cardvec[i] = vec[i];
+        __syncthreads();
+    }
+    uint32_t *wtile = dyn_tile + warp * (OBS_TILE_BYTES / 4);           // this warp's 32 dense byte rows
+    uint32_t *wrow = wtile + ((lane * SPL_OBS_SIZE) >> 2);              // the word that holds this lane's byte 0
+    const uint32_t sh = 8u * (lane & 3);
+    for (; base < N; base += stride) {
         const int64_t i = base + lane;
+        Env<P> e = nxt;
+        const int eseat = nseat;
+        if (i + stride < N) {
+            load_env(nxt, state, N, i + stride);
+            if (seat) nseat = seat[i + stride];
+        }
+        uint32_t first = 0, last = 0, spill0 = 0, spill1 = 0, head4 = 0, head5 = 0;
         if (i < N) {
-            Env<P> e;
-            load_env(e, state, N, i);
             uint32_t o[OBS_WORDS + 1];
 #pragma unroll
             for (int w = 0; w <= OBS_WORDS; w++) o[w] = 0;
-            thread_fill_obs(e, sT, seat ? (int)seat[i] : seat_of(e.meta), o, ObsRowSink{wtile + lane * OBS_WORDS, o});
+            thread_fill_obs(e, sT, seat ? eseat : seat_of(e.meta), o, ObsDenseSink{wrow, o, sh});
+            first = o[0] << sh;
+            last = __funnelshift_l(o[65], o[66] & 0xFFu, sh);
+            spill0 = o[66]; spill1 = o[67]; head4 = o[4]; head5 = o[5];  // the special entries' sources (bytes 265..268, 19..23)
         }
+        // the two boundary words of each row: a row's last bytes share a word with the next row's first ones
+        const uint32_t prev_last = __shfl_up_sync(0xFFFFFFFFu, last, 1);
+        wrow[0] = (lane & 3) ? (first | prev_last) : first;
+        if ((lane & 3) == 3) wrow[66] = last;
         __syncwarp();
-        obs_tile_store(reinterpret_cast<const uint8_t *>(wtile), obs + base * SPL_OBS_SIZE, (int)min((int64_t)32, N - base), lane);
+        obs_tile_store(wtile, obs + base * SPL_OBS_SIZE, (int)min((int64_t)32, N - base), lane);
         __syncwarp();  // orders the plain stores of every lane before the owners' patches of the same addresses
-        if (i < N) obs_patch_special(reinterpret_cast<const uint8_t *>(wtile) + lane * OBS_ROW_BYTES, obs + i * SPL_OBS_SIZE);
+        if (i < N) {
+            float *dst = obs + i * SPL_OBS_SIZE;
+            dst[1] = (float)((spill0 >> 24) | (spill1 & 0xFFu) << 8);                 // turns (bytes 267, 268)
+            dst[6] = __fdiv_rn((float)((spill0 >> 8) & 0xFFFFu), 25.0f);              // np.var numerator (bytes 265, 266) / 25
+            dst[19] = __uint_as_float(g_log1p_bits[(head4 >> 24) & 31u]);
+#pragma unroll
+            for (int n = 0; n < 4; n++) dst[20 + n] = __uint_as_float(g_log1p_bits[(head5 >> (8 * n)) & 31u]);
+        }
         __syncwarp();
     }
 }
@@ -904,25 +990,6 @@ static unsigned persistent_grid(int64_t n, int blocks_per_sm)
     return (unsigned)(want < cap ? want : cap);
 }
 
-// tile kernels: block size (a multiple of 32, overridable for experiments), dynamic shared memory above 48 KB, residency
-static int tile_block(const char *env_name, int dflt)
-{
-    const char *v = getenv(env_name);
-    const int tb = v ? atoi(v) : dflt;
-    return (tb >= 32 && tb <= TILE_TB_MAX && tb % 32 == 0) ? tb : dflt;
-}
-template <class K>
-static cudaError_t allow_smem(K kernel, size_t dyn_bytes)
-{
-    return dyn_bytes + sizeof(Tables) > 48 * 1024 ? cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes)
-                                                  : cudaSuccess;
-}
-static int resident_blocks(size_t dyn_bytes)  // per SM, by shared memory (227 KB usable, 1 KB reserved per block)
-{
-    const int n = (int)((227 * 1024) / (dyn_bytes + sizeof(Tables) + 1024));
-    return n < 1 ? 1 : n;
-}
-
 #define DISPATCH_P(P, ...)             \
     switch (P) {                       \
     case 2: { constexpr int PP = 2; __VA_ARGS__; } break; \
@@ -1008,25 +1075,62 @@ int spl_inject(void *state, const uint8_t *deck_lists, const uint8_t *nobles, in
     return SPL_OK;
 }
 
-// persistent row kernels: as many blocks as the tile lets reside, each warp strides over 32-env groups
+// Persistent row kernels: every warp strides over 32-env tiles, so a launch lasts ceil(tiles / resident warps) tile times
+// and a tile takes longer the more warps share the SM.  Among the (warps per block) x (blocks per SM) shapes whose tiles
+// and tables fit the SM's shared memory, take the one with the smallest rounds x (warps per SM + ROW_LATENCY_WARPS) - the
+// second factor models a tile time that is part latency, part issue contention (calibrated on 262,144 and 2^20 envs,
+// profiles/r2_kernels.md).  SPL_MASK_SHAPE / SPL_OBS_SHAPE = "<warps per block>x<blocks per SM>" overrides it.
+struct RowShape { int warps_per_block, blocks_per_sm; };
+constexpr int ROW_LATENCY_WARPS = 8;
+static RowShape row_shape(int64_t N, size_t tile_bytes, size_t table_bytes, int regs_per_thread, const char *env_name, int block_warps = 0,
+                          int max_blocks_per_sm = 4)
+{
+    const int warp_regs = 32 * ((regs_per_thread + 7) & ~7);  // registers are allocated per warp, eight per thread at a time
+    const auto fits = [&](int wb, int nb) {
+        return wb >= 1 && wb * 32 <= TILE_TB_MAX && nb >= 1 && nb <= 8 && nb * wb * warp_regs <= 65536 &&
+               (size_t)nb * (wb * tile_bytes + table_bytes + 1024) <= 227u * 1024u;
+    };
+    if (const char *v = getenv(env_name)) {
+        int wb = 0, nb = 0;
+        if (sscanf(v, "%dx%d", &wb, &nb) == 2 && fits(wb, nb)) return RowShape{wb, nb};
+    }
+    const int64_t tiles = (N + 31) / 32, sms = sm_count();
+    RowShape best{1, 1};
+    int64_t best_cost = INT64_MAX;
+    for (int nb = 1; nb <= max_blocks_per_sm; nb++)
+        for (int wb = block_warps ? block_warps : 1; fits(wb, nb) && (!block_warps || wb == block_warps); wb++) {
+            const int w = wb * nb;
+            const int64_t rounds = (tiles + sms * w - 1) / (sms * w), cost = rounds * (w + ROW_LATENCY_WARPS);
+            if (cost < best_cost || (cost == best_cost && nb < best.blocks_per_sm)) { best_cost = cost; best = RowShape{wb, nb}; }
+        }
+    return best;
+}
 static int launch_mask(const void *state, const int8_t *seat, uint32_t *mask, int64_t N, int P, cudaStream_t stream)
 {
-    static const int tb = tile_block("SPL_MASK_BLOCK", MASK_TB);
+    cudaFuncAttributes attr;
+    DISPATCH_P(P, CK(cudaFuncGetAttributes(&attr, legal_mask_kernel<PP>)));
+    const RowShape sh = row_shape(N, 32 * MASK_ROW_BYTES, TABLES_MASK_BYTES, attr.numRegs, "SPL_MASK_SHAPE");
+    const int tb = 32 * sh.warps_per_block;
     const size_t smem = (size_t)tb * MASK_ROW_BYTES;
-    const int64_t want = (N + tb - 1) / tb, cap = (int64_t)sm_count() * resident_blocks(smem);
+    const int64_t want = (N + tb - 1) / tb, cap = (int64_t)sm_count() * sh.blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    DISPATCH_P(P, CK(allow_smem(legal_mask_kernel<PP>, smem));
+    DISPATCH_P(P, CK(cudaFuncSetAttribute(legal_mask_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                legal_mask_kernel<PP><<<grid, tb, smem, stream>>>((const uint4 *)state, seat, mask, N));
     CK(cudaGetLastError());
     return SPL_OK;
 }
 static int launch_observe(const void *state, const int8_t *seat, float *obs, int64_t N, int P, cudaStream_t stream)
 {
-    static const int tb = tile_block("SPL_OBS_BLOCK", OBS_TB);
-    const size_t smem = (size_t)tb * OBS_ROW_BYTES;
-    const int64_t want = (N + tb - 1) / tb, cap = (int64_t)sm_count() * resident_blocks(smem);
+    cudaFuncAttributes attr;
+    DISPATCH_P(P, CK(cudaFuncGetAttributes(&attr, observe_kernel<PP>)));
+    // blocks of four warps - one per scheduler - and at most five of them per SM: measured best at 262,144 and 2^20 envs
+    // (bigger blocks run their build / store phases in step; 24 warps only add contention once DRAM writes are the limit)
+    const RowShape sh = row_shape(N, OBS_TILE_BYTES, sizeof(ObsTables), attr.numRegs, "SPL_OBS_SHAPE", 4, 5);
+    const int tb = 32 * sh.warps_per_block;
+    const size_t smem = (size_t)sh.warps_per_block * OBS_TILE_BYTES;
+    const int64_t want = (N + tb - 1) / tb, cap = (int64_t)sm_count() * sh.blocks_per_sm;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    DISPATCH_P(P, CK(allow_smem(observe_kernel<PP>, smem));
+    DISPATCH_P(P, CK(cudaFuncSetAttribute(observe_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                observe_kernel<PP><<<grid, tb, smem, stream>>>((const uint4 *)state, seat, obs, N));
     CK(cudaGetLastError());
     return SPL_OK;
@@ -1198,35 +1302,10 @@ int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t firs
     DISPATCH_P(P, env_move_kernel<PP><<<persistent_grid(N, ENV_MOVE_BLOCKS_PER_SM), ENV_TB, 0, (cudaStream_t)stream>>>(
                       (uint4 *)state, decks, seed, first_game, game_ids, learner, action, reward, terminated, illegal, N, flags));
     CK(cudaGetLastError());
-    // The two row kernels only READ the states the move kernel wrote and write different outputs, so they go out on two
-    // streams - the mask kernel on a library-owned side stream, the observation kernel on the caller's, which then waits
-    // for both: the ramp-down of one persistent grid overlaps the ramp-up of the other (0.1297 -> 0.1212 ms per 262,144
-    // envs; capping the grids so that both are fully co-resident measured slower, profiles/r2_kernels.md).  Per device;
-    // `stream` semantics are unchanged: everything is ordered after the work queued before the call and complete when the
-    // stream reaches the end of the call.
-    static int overlap = -1;
-    if (overlap < 0) { const char *v = getenv("SPL_ENV_OVERLAP"); overlap = v ? atoi(v) : 1; }
-    if (obs && mask && overlap && N >= 32768) {
-        int dev = 0;
-        CK(cudaGetDevice(&dev));
-        if (dev < 0 || dev >= SPL_MAX_DEVICES) return SPL_E_BADARG;
-        static cudaStream_t side[SPL_MAX_DEVICES] = {};
-        static cudaEvent_t ev_fork[SPL_MAX_DEVICES] = {}, ev_join[SPL_MAX_DEVICES] = {};
-        static std::mutex mu;
-        std::lock_guard<std::mutex> lock(mu);
-        if (!side[dev]) {
-            CK(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
-        }
-        CK(cudaEventRecord(ev_fork[dev], (cudaStream_t)stream));
-        CK(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
-        if (int rc = launch_mask(state, seat, mask, N, P, side[dev])) return rc;
-        CK(cudaEventRecord(ev_join[dev], side[dev]));
-        if (int rc = launch_observe(state, seat, obs, N, P, (cudaStream_t)stream)) return rc;
-        CK(cudaStreamWaitEvent((cudaStream_t)stream, ev_join[dev], 0));
-        return SPL_OK;
-    }
+    // The two row kernels follow in plain stream order.  (Round 2 ran the mask kernel on a side stream: with the row kernels'
+    // present shapes the two grids then fight for shared memory and the persistent blocks that start late finish late -
+    // 0.122 ms against 0.111 per 262,144 envs; programmatic dependent launch of one behind the other: no difference,
+    // profiles/r2_kernels.md.)
     if (obs)
         if (int rc = launch_observe(state, seat, obs, N, P, (cudaStream_t)stream)) return rc;
     if (mask)  // the LEARNER's mask (get_legal_actions_mask uses my_turn, splendor_env.py:184)

@@ -16,6 +16,7 @@ ap.add_argument("--envs", type=int, nargs="+", default=[262144])
 ap.add_argument("--players", type=int, default=2)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--advance", type=int, default=30, help="env-steps played before timing (mid-game states)")
+ap.add_argument("--only", nargs="+", default=None, help="time only these kernels (legal_mask observe step env_step masked_sample)")
 a = ap.parse_args()
 PEAK = 6533.8
 
@@ -52,8 +53,11 @@ for N in a.envs:
     mask_buf = torch.empty((N, 110), dtype=torch.int32, device=eng.device)
     obs_buf = torch.empty((N, 265), dtype=torch.float32, device=eng.device)
     res = {}
-    res["legal_mask"] = (timed(lambda: eng.legal_mask(out=mask_buf), a.reps), W + 440)
-    res["observe"] = (timed(lambda: eng.observe(out=obs_buf), a.reps), W + 1060)
+    want = lambda k: a.only is None or k in a.only  # noqa: E731
+    if want("legal_mask"):
+        res["legal_mask"] = (timed(lambda: eng.legal_mask(out=mask_buf), a.reps), W + 440)
+    if want("observe"):
+        res["observe"] = (timed(lambda: eng.observe(out=obs_buf), a.reps), W + 1060)
 
     def timed_after_restore(fn, reps):
         """state-changing kernels: {restore the saved states; call} captured in a CUDA graph and replayed back to back, minus
@@ -81,8 +85,10 @@ for N in a.envs:
 
         return graph_ms(lambda: (eng.state.copy_(saved), fn())) - graph_ms(lambda: eng.state.copy_(saved))
 
-    res["step"] = (timed_after_restore(lambda: eng.step(act), a.reps), 2 * W + 2 + 3)
-    res["env_step"] = (timed_after_restore(lambda: eng.env_step(learner, act), a.reps), 2 * W + 440 + 1060 + 3 + 3)
+    if want("step"):
+        res["step"] = (timed_after_restore(lambda: eng.step(act), a.reps), 2 * W + 2 + 3)
+    if want("env_step"):
+        res["env_step"] = (timed_after_restore(lambda: eng.env_step(learner, act), a.reps), 2 * W + 440 + 1060 + 3 + 3)
     for k, (ms, bytes_per_env) in res.items():
         gbs = N * bytes_per_env / (ms * 1e-3) / 1e9
         print(json.dumps({"kernel": k, "envs": N, "players": P, "ms": ms, "envs_per_s": N / (ms * 1e-3), "bytes_per_env": bytes_per_env,
@@ -91,7 +97,7 @@ for N in a.envs:
 # masked action sampling (spl_masked_sample): 3510 float32 logits + 110 mask words per row
 from splendor_ai_b200.sampling import masked_sample  # noqa: E402
 
-for N in a.envs:
+for N in (a.envs if a.only is None or "masked_sample" in a.only else []):
     rows = min(N, 262144)
     logits = torch.randn((rows, 3510), device="cuda")
     eng = pkg.BatchedSplendor(rows, a.players, seed=1)
