@@ -159,7 +159,8 @@ int spl_observe(const void *state, const int8_t *seat, float *obs, int64_t N, in
 
 /* Whole random playouts that never leave the GPU: Game.Run with RandomAgents (game.py:104-213,
  * agents/generic/random.py:21-27) for games first_game .. first_game+num_games-1, fused reset + legal-count + uniform
- * choice (Philox word of (seed, game, step) scaled to the count, k-th legal action in ascending ALL_ACTIONS order)
+ * choice (word step & 3 of the Philox block (seed, game, step >> 2, stream 0) scaled to the count - one block serves four
+ * consecutive moves -, k-th legal action in ascending ALL_ACTIONS order)
  * + step + terminal + calScore.  Outputs (all optional): score2 [G][P], steps [G], end_kind [G], counters[16]
  * (accumulated), trace [trace_len][G] = action index taken at step t (-1 after the end), final_state (packed layout,
  * N = num_games).  max_steps in 1..4096.

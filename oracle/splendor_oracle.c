@@ -650,8 +650,8 @@ int orc_playout(uint64_t seed, uint64_t game, int P, int limit_rounds, int max_s
     while (t < max_steps && !(e = orc_game_ends(&s, limit_rounds))) {
         int n = orc_legal(&s, s.cur, legal);
         uint32_t w[4];
-        orc_philox(seed, game, (uint32_t)t, STREAM_ACTION, w);
-        int a = legal[mulhi(w[0], (uint32_t)n)];
+        orc_philox(seed, game, (uint32_t)t >> 2, STREAM_ACTION, w);  /* one Philox block serves four consecutive moves */
+        int a = legal[mulhi(w[t & 3], (uint32_t)n)];
         if (trace) trace[t] = (int16_t)a;
         orc_step(&s, a);
         t++;

@@ -390,6 +390,9 @@ __device__ __forceinline__ uint4 philox_rk(const uint32_t *__restrict__ rk, uint
     return make_uint4(c0, c1, c2, c3);
 }
 enum Stream { STREAM_ACTION = 0, STREAM_DECK0 = 1, STREAM_NOBLES = 4, STREAM_ENV = 5 };
+// The playouts' action draw for move t of a game: word t & 3 of the Philox block (seed, game, t >> 2, STREAM_ACTION) - one
+// block serves four consecutive moves (the env kernels' in-kernel opponents draw word 0 of block (seed, game, total turns)).
+__host__ __device__ inline uint32_t word_of(const uint4 &v, uint32_t i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 // ------------------------------------------------------------------------------------------------ state in registers
 constexpr uint32_t META_EXPLICIT = 1u << 24, META_ILLEGAL = 1u << 26;

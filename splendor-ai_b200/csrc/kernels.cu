@@ -172,6 +172,9 @@ __device__ __forceinline__ uint32_t turns_total(const Env<P> &e)
 #ifndef SPL_POOL_STEPS
 #define SPL_POOL_STEPS 8
 #endif
+#ifndef SPL_POOL_SPREAD
+#define SPL_POOL_SPREAD 8  // at most this many live games in a block: one per warp (<= SPL_POOL_WARPS - 2)
+#endif
 
 template <int P, int NW>
 struct PoolSmem {
@@ -180,6 +183,7 @@ struct PoolSmem {
     uint32_t gid[2][CAP];  // game index inside the launch
     uint32_t t0[2][CAP];   // total turns when the game entered the pool (0 for fresh games)
     Tables T;
+    uint4 rnd[CAP][3];     // per thread: the Philox blocks its game's action draws of this round come from (four moves per block)
     unsigned int ctr[16];  // block-level counters (32 bits are enough for one block of one launch)
     int n_alive[3];        // list lengths, rotating: read in round r, appended to for round r+1, zeroed for round r+2
 };
@@ -257,14 +261,18 @@ __global__ void __launch_bounds__(32 * NW, SPL_POOL_BLOCKS_PER_SM) playout_pool_
     for (int round = 0, r3 = 0;; round++, r3 = r3 == 2 ? 0 : r3 + 1) {
         const int b = round & 1, r3n = r3 == 2 ? 0 : r3 + 1, r3z = r3n == 2 ? 0 : r3n + 1;
         const int nA = S.n_alive[r3];
-        const int n_step = min(nA, SCAP), chunks = (n_step + 31) >> 5, carried = nA - n_step;
+        // The last few games of a block are SPREAD: one game per warp (lane 0) instead of all in one warp - a warp runs the
+        // union of its lanes' paths one after the other, and at the end of a launch the step latency of the longest games
+        // is all that is left.
+        const bool spread = nA <= SPL_POOL_SPREAD;
+        const int n_step = min(nA, SCAP), chunks = spread ? nA : (n_step + 31) >> 5, carried = nA - n_step;
         // new games this round: the keeper's free lanes first, then 32 per idle stepping warp; never more than fit the list
         const int room = min(min(CAP - nA, n_mine - started), (32 - carried) + 32 * (NW - 1 - chunks));
         if (nA == 0 && room == 0) break;
         if (threadIdx.x == 0) S.n_alive[r3z] = 0;  // last read in the previous round, next appended to in the next one
         const bool keeper = warp == NW - 1, stepper = warp < chunks;
-        const int p = keeper ? SCAP + lane : warp * 32 + lane;
-        const bool valid = keeper ? lane < carried : (stepper && p < n_step);
+        const int p = keeper ? SCAP + lane : (spread ? warp : warp * 32 + lane);
+        const bool valid = keeper ? lane < carried : (stepper && (spread ? lane == 0 : p < n_step));
         // fresh-game slot of this lane: keeper lanes carried .. 31 -> 0 .., idle stepping warp j -> (32 - carried) + 32 j + lane
         const int j_new = keeper ? lane - carried : (32 - carried) + (warp - chunks) * 32 + lane;
         const bool loading = !valid && !stepper && j_new >= 0 && j_new < room;
@@ -274,6 +282,7 @@ __global__ void __launch_bounds__(32 * NW, SPL_POOL_BLOCKS_PER_SM) playout_pool_
         // its warps play one move more per round (games are independent, so rounds need not be the same length for all)
         const int heavy = (chunks + 3) >> 2, mine = (chunks - (warp & 3) + 3) >> 2;
         const int n_steps = SPL_POOL_STEPS + ((chunks & 3) && mine < heavy ? 1 : 0);
+        static_assert(SPL_POOL_STEPS + 1 + 3 <= 12, "three Philox blocks cover a round's action draws from any phase");
         if (stepper || keeper || room > 0) {  // warp-uniform: a warp with nothing to do goes straight to the barrier
             Env<P> e;
             uint32_t gid = 0, t0 = 0;
@@ -289,14 +298,22 @@ __global__ void __launch_bounds__(32 * NW, SPL_POOL_BLOCKS_PER_SM) playout_pool_
                     t = (int)turns_total(e);
                     const int t_end = (int)t0 + a.max_steps;
                     if (MODE == POOL_STATES) kind = game_ends(e, a.flags);  // a game that was over when it was handed in
+                    // The round's action draws up front, all lanes at once: move t takes word t & 3 of Philox block t >> 2, so
+                    // two blocks (three when the game is mid-block or the round has nine moves) serve the whole round - the
+                    // generator is out of the divergent step loop and runs 2-3 times per round instead of 8-9.
+                    const uint32_t blk = (uint32_t)t >> 2;
+                    S.rnd[threadIdx.x][0] = philox_rk(a.rk, game, blk, STREAM_ACTION);
+                    S.rnd[threadIdx.x][1] = philox_rk(a.rk, game, blk + 1, STREAM_ACTION);
+                    if ((t & 3) + n_steps > 8) S.rnd[threadIdx.x][2] = philox_rk(a.rk, game, blk + 2, STREAM_ACTION);
+                    const uint32_t *draws = reinterpret_cast<const uint32_t *>(&S.rnd[threadIdx.x][0]) - 4 * blk;  // draws[t]
 #pragma unroll 1
                     for (int s = 0; s < n_steps && kind == SPL_END_NONE; s++) {
                         Ctx c;
                         FamilyCounts f;
                         Choice ch;
-                        const uint32_t r = philox_rk(a.rk, game, (uint32_t)t, STREAM_ACTION).x;
                         make_ctx<P, true>(e, T, c);
                         const int total = count_legal(e, T, c, f);
+                        const uint32_t r = draws[t];
                         select_legal(e, T, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
                         if (__builtin_expect(t < a.trace_len, 0)) a.trace[(int64_t)t * a.n_games + gid] = (int16_t)ch.idx;
                         apply_action<P, false, true>(e, ch, src);

@@ -179,7 +179,7 @@ template <int P> static int t_playout(uint32_t *w, bool fresh, const uint8_t *li
         Ctx c; FamilyCounts f; Choice ch;
         make_ctx(e, T, c);
         const int total = count_legal(e, T, c, f);
-        const uint32_t r = philox_rk(rk, game, (uint32_t)t, STREAM_ACTION).x;
+        const uint32_t r = word_of(philox_rk(rk, game, (uint32_t)t >> 2, STREAM_ACTION), (uint32_t)t & 3u);
         select_legal(e, T, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
         if (trace && t < trace_len) trace[t] = (int16_t)ch.idx;
         if (fresh) apply_action<P, true>(e, ch, src); else apply_action(e, ch, src);
