@@ -1001,6 +1001,89 @@ __device__ __forceinline__ bool decode_and_check(const Env<P> &e, const Tables &
     return decode_and_check(e, T, c, idx, ch, T);
 }
 
+// ---- the same membership test with the index decoded by TABLE (the step kernels): every family's divisions and remainders
+// of the index above become one 16-byte row read, identical code for all 32 lanes of a warp, and collect_same /
+// collect_diff share one check.  Row of index i:  .x = gems collected, .y = gems returned (both g6; zero for buys),
+// .z = type | slot << 3 | noble slot << 11 | gems taken << 15 (2 for collect_same, the combo's length for collect_diff)
+//      | the length tested against Lmin << 18 (7 = always passes, for collect_same) | reserve variant << 21,
+// .w = colour-field mask that must be available (collect: the colours taken; reserve: the colour handed back, if any).
+struct DecodeTable { uint4 row[SPL_NUM_ACTIONS]; };
+__host__ __device__ constexpr DecodeTable make_decode_table(const Tables &T)
+{
+    DecodeTable D{};
+    for (int idx = 0; idx < SPL_NUM_ACTIONS; idx++) {
+        uint32_t C = 0, R = 0, type = T_PASS, slot = 0, n = 0, take = 0, lchk = 7, v = 0, need = 0;
+        if (idx < BASE_RESERVE) {
+            n = (uint32_t)idx;
+        } else if (idx < BASE_SAME) {
+            const int r = idx - BASE_RESERVE;
+            type = T_RESERVE; slot = (uint32_t)(r / 42); n = (uint32_t)((r % 42) / 7); v = (uint32_t)(r % 7);
+            if (v >= 1) C = 1u << YSH;
+            if (v >= 2) { const int fl = field_of_normal((int)v - 2); R = 1u << (5 * fl); need = 1u << fl; }
+        } else if (idx < BASE_DIFF) {
+            const int r = idx - BASE_SAME, col = r / 126, fl = field_of_normal(col);
+            type = T_SAME; slot = (uint32_t)col; n = (uint32_t)((r % 126) / 21); take = 2;
+            C = 2u << (5 * fl); R = T.ret_same[col * 21 + r % 21]; need = 1u << fl;
+        } else if (idx < BASE_BUY_RESERVE) {
+            const int r = idx - BASE_DIFF;
+            int ci = 0, rem = 0, V = 0;
+            if (r < 180) { ci = r / 36; rem = r % 36; V = 6; }
+            else if (r < 1080) { ci = 5 + (r - 180) / 90; rem = (r - 180) % 90; V = 15; }
+            else { ci = 15 + (r - 1080) / 120; rem = (r - 1080) % 120; V = 20; }
+            const int L = ci < 5 ? 1 : (ci < 15 ? 2 : 3);
+            type = T_DIFF; slot = (uint32_t)ci; n = (uint32_t)(rem / V); take = (uint32_t)L; lchk = (uint32_t)L;
+            C = T.combo_c[ci]; R = T.ret_diff[T.combo_off[ci] + rem % V]; need = T.combo_mask[ci];
+        } else {
+            const bool avail = idx >= BASE_BUY_AVAILABLE;
+            const int r = idx - (avail ? BASE_BUY_AVAILABLE : BASE_BUY_RESERVE);
+            type = avail ? T_BUY_AVAILABLE : T_BUY_RESERVE; slot = (uint32_t)(r / 6); n = (uint32_t)(r % 6);
+        }
+        D.row[idx] = uint4{C, R, type | slot << 3 | n << 11 | take << 15 | lchk << 18 | v << 21, need};
+    }
+    return D;
+}
+// `row` = DecodeTable::row[idx] for a valid idx (anything for an invalid one); the caller may have loaded it early
+template <int P>
+__device__ __forceinline__ bool decode_and_check_row(const Env<P> &e, const Tables &T, const Ctx &c, int idx, const uint4 &row, Choice &ch,
+                                                     const Tables &Tcount)
+{
+    ch.idx = idx; ch.C = 0; ch.R = 0; ch.info = 0; ch.slot = 0; ch.n = 0; ch.type = T_PASS;
+    if (idx < 0 || idx >= SPL_NUM_ACTIONS) return false;
+    ch.C = row.x; ch.R = row.y;
+    ch.type = (int)(row.z & 7u); ch.slot = (int)((row.z >> 3) & 255u); ch.n = (int)((row.z >> 11) & 15u);
+    bool ok;
+    uint32_t S = c.S;
+    if (ch.type == T_PASS) {
+        FamilyCounts f;
+        ok = count_legal(e, Tcount, c, f) == 0;
+    } else if (ch.type == T_RESERVE) {
+        const int v = (int)((row.z >> 21) & 7u);
+        int expect_lo, expect_hi;
+        if (!c.bank_yellow) expect_lo = expect_hi = 0;
+        else if (c.hold < 10) expect_lo = expect_hi = 1;
+        else { expect_lo = 2; expect_hi = 6; }
+        ok = c.n_resv < 3 && (c.occ >> ch.slot & 1) && v >= expect_lo && v <= expect_hi && !(row.w & ~c.h1);
+    } else if (ch.type <= T_DIFF) {  // collect_same (two of a colour with >= 4 in the bank) or collect_diff (one each)
+        const uint32_t avail = ch.type == T_SAME ? c.A4 : c.A1;
+        const int take = (int)((row.z >> 15) & 7u), lchk = (int)((row.z >> 18) & 7u);
+        ok = !(row.w & ~avail) && lchk >= c.Lmin && (int)hsum6(ch.R) == max(c.hold + take - 10, 0) && satsub6(ch.R, c.gems) == 0;
+    } else {
+        const bool avail = ch.type == T_BUY_AVAILABLE;
+        const int s = ch.slot;
+        uint32_t w = e.d[0];
+        if ((s >> 2) == 1) w = e.d[1];
+        if ((s >> 2) == 2) w = e.d[2];
+        const uint32_t id = avail ? byte_of(w, s & 3) : byte_of(c.resv, s);
+        ok = id != NONE8;
+        const uint2 cw = T.card[id & 127u];
+        ok = ok && can_buy(c, cw, ch.R);
+        ch.info = cw.y;
+        S |= (c.near >> (cw.y & 31u)) & 31u;
+    }
+    const bool noble_ok = S ? (ch.n >= 1 && (S >> (ch.n - 1) & 1)) : ch.n == 0;
+    return ok && noble_ok;
+}
+
 // ------------------------------------------------------------------------------------------------ successor
 // generateSuccessor + GameRule.update.  Returns the acting agent's score delta.
 template <int P, bool LISTS = false, bool MOVER0 = false>

@@ -32,6 +32,8 @@ namespace spl {
 
 __device__ const Tables g_tables = make_tables();
 __device__ const uint32_t g_log1p_bits[32] = SPL_LOG1P_BITS;
+__device__ const DecodeTable g_decode = make_decode_table(make_tables());  // 56 KB, read through L2 by the step kernels
+__device__ __forceinline__ uint4 decode_row(int a) { return g_decode.row[min(max(a, 0), SPL_NUM_ACTIONS - 1)]; }
 
 constexpr int BLOCK = 128;
 
@@ -367,9 +369,11 @@ __global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Env<P> e;
     int a = -1;
+    uint4 row = make_uint4(0, 0, 0, 0);  // the action's decoded fields (engine.cuh DecodeTable), loaded with the state
     if (i < N) {
         a = action[i];
         load_env(e, state, N, i);
+        row = decode_row(a);
     }
     stage_tables_nosync(sT, 0, TABLES_STEP_BYTES);  // decode + apply read a quarter of the tables
     __syncthreads();
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_
             Ctx c;
             Choice ch;
             make_ctx(e, sT, c);
-            if (decode_and_check(e, sT, c, a, ch, g_tables)) {  // (a pass is checked against the complete tables in global memory)
+            if (decode_and_check_row(e, sT, c, a, row, ch, g_tables)) {  // (a pass is checked against the complete tables in global memory)
                 const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
                 rew = apply_action(e, ch, src);
             } else {
@@ -396,6 +400,7 @@ __global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_
         if (i < N) {
             a = action[i];
             load_env(e, state, N, i);
+            row = decode_row(a);
         }
     }
 }
@@ -802,10 +807,12 @@ __global__ void __launch_bounds__(ENV_TB) env_move_kernel(uint4 *state, const ui
     const bool self_play = flags & SPL_F_SELF_PLAY;
     Env<P> e;
     int a = -1, me = 0;
+    uint4 row = make_uint4(0, 0, 0, 0);
     if (i < N) {  // the first env's loads go out before the table copy and its barrier
         a = action[i];
         me = self_play ? 0 : (int)learner[i];
         load_env(e, state, N, i);
+        row = decode_row(a);
     }
     stage_tables_nosync(sT);
     __syncthreads();
@@ -818,7 +825,7 @@ __global__ void __launch_bounds__(ENV_TB) env_move_kernel(uint4 *state, const ui
             Ctx c;
             Choice ch;
             make_ctx(e, sT, c);
-            if (seat_of(e.meta) == me && game_ends(e, flags) == SPL_END_NONE && decode_and_check(e, sT, c, a, ch))
+            if (seat_of(e.meta) == me && game_ends(e, flags) == SPL_END_NONE && decode_and_check_row(e, sT, c, a, row, ch, sT))
                 rew = apply_action(e, ch, src);
             else { bad = 1; go = false; e.meta |= META_ILLEGAL; }
         }
@@ -842,6 +849,7 @@ __global__ void __launch_bounds__(ENV_TB) env_move_kernel(uint4 *state, const ui
             a = action[i];
             me = self_play ? 0 : (int)learner[i];
             load_env(e, state, N, i);
+            row = decode_row(a);
         }
     }
 }

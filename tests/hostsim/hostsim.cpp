@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #define __device__
@@ -42,6 +44,7 @@ using std::min;
 
 using namespace spl;
 static const Tables T = make_tables();
+static const DecodeTable DEC = make_decode_table(T);  // the step kernels' table-driven decode
 static const uint32_t LOG1P[32] = SPL_LOG1P_BITS;
 
 #define DISPATCH(P, ...)                                   \
@@ -105,7 +108,17 @@ template <int P> static int t_legal_member(const uint32_t *w, uint16_t *out)
     Ctx c; Choice ch;
     make_ctx(e, T, c);
     int n = 0;
-    for (int idx = 0; idx < SPL_NUM_ACTIONS; idx++) if (decode_and_check(e, T, c, idx, ch)) out[n++] = (uint16_t)idx;
+    for (int idx = 0; idx < SPL_NUM_ACTIONS; idx++) {
+        // both membership forms - index arithmetic and the table row - must agree on the verdict and on every decoded field
+        Choice ch2;
+        const bool ok = decode_and_check(e, T, c, idx, ch), ok2 = decode_and_check_row(e, T, c, idx, DEC.row[idx], ch2, T);
+        if (ok != ok2 || (ok && (ch.type != ch2.type || ch.slot != ch2.slot || ch.n != ch2.n || ch.C != ch2.C || ch.R != ch2.R ||
+                                 ch.info != ch2.info || ch.idx != ch2.idx))) {
+            std::fprintf(stderr, "hostsim: decode forms disagree at index %d\n", idx);
+            std::abort();
+        }
+        if (ok) out[n++] = (uint16_t)idx;
+    }
     return n;
 }
 template <int P> static int t_mask(const uint32_t *w, int seat, uint32_t *mask)
@@ -126,7 +139,8 @@ template <int P> static int t_step(uint32_t *w, const uint8_t *lists, uint64_t s
     make_ctx(e, T, c);
     int bad = 0;
     *reward = 0;
-    if (decode_and_check(e, T, c, idx, ch)) { const DeckSrc src{lists, seed, game}; *reward = apply_action(e, ch, src); }
+    const uint4 row = DEC.row[std::min(std::max(idx, 0), SPL_NUM_ACTIONS - 1)];  // as step_kernel does
+    if (decode_and_check_row(e, T, c, idx, row, ch, T)) { const DeckSrc src{lists, seed, game}; *reward = apply_action(e, ch, src); }
     else { bad = 1; e.meta |= META_ILLEGAL; }
     st(e, w);
     *done = game_ends(e, flags);

@@ -326,6 +326,30 @@ def test_ragged_batches_take_the_plain_store_path(pkg, oracle, N):
         assert np.array_equal(obs[e].view(np.uint32), oracle.observe(orcs[e], orcs[e].cur).view(np.uint32)), e
 
 
+@pytest.mark.parametrize("N,P", [(70, 2), (131, 3), (96, 4)])
+def test_observation_buffer_that_is_only_float_aligned(pkg, oracle, N, P):
+    """The observation kernel writes a warp's 32 rows as 128-bit stores when the caller's buffer is 16-byte aligned and falls
+    back to scalar stores when it is not: both must give the same bits, and neither may write outside the N rows."""
+    eng = pkg.BatchedSplendor(N, P, seed=5, first_game=900, limit_rounds=True)
+    learner = torch.zeros(N, dtype=torch.int8, device=eng.device)
+    act = torch.full((N,), -1, dtype=torch.int16, device=eng.device)
+    gen = torch.Generator(device=eng.device).manual_seed(3)
+    for _ in range(12):  # mid-game states
+        _, _, _, _, mask = eng.env_step(learner, act)
+        act = torch.multinomial(pkg.env.unpack_mask(mask, torch.float32), 1, generator=gen).squeeze(1).to(torch.int16)
+    want = eng.observe()
+    flat = torch.full((N * 265 + 8,), float("nan"), dtype=torch.float32, device=eng.device)
+    for off in (1, 2, 3, 4):
+        flat.fill_(float("nan"))
+        view = flat[off:off + N * 265].view(N, 265)
+        assert view.data_ptr() % 16 == (4 * off) % 16
+        got = eng.observe(out=view)
+        assert torch.equal(got.view(torch.int32), want.view(torch.int32)), off
+        assert torch.isnan(flat[:off]).all() and torch.isnan(flat[off + N * 265:]).all(), off
+    seats = torch.from_numpy(np.random.default_rng(1).integers(0, P, N).astype(np.int8)).cuda()
+    assert torch.equal(eng.observe(seat=seats, out=flat[1:1 + N * 265].view(N, 265)).view(torch.int32), eng.observe(seat=seats).view(torch.int32))
+
+
 @pytest.mark.parametrize("P", [2, 3, 4])
 def test_env_step_matches_oracle_emulation_of_splendor_env(pkg, oracle, P):
     """spl_env_step vs SplendorEnv.step semantics (splendor_env.py:127-231) emulated with the oracle: learner move,
