@@ -1,37 +1,29 @@
 """Time the single-call kernels (legal mask, step, observe, fused PPO env-step) on mid-game states and report achieved
-HBM GB/s against algorithmic bytes.  Usage: python tools/perf_kernels.py [--envs 262144] [--players 2] [--reps 20]"""
+HBM GB/s against algorithmic bytes: per-launch times on cold data, tools/cold_timing.py.
+Usage: python tools/perf_kernels.py [--envs 262144] [--players 2] [--reps 5] [--only legal_mask observe step env_step masked_sample]"""
 import argparse
 import json
 import os
 import sys
 
+import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import splendor_ai_b200 as pkg
 from splendor_ai_b200.env import unpack_mask
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from cold_timing import per_launch_ms  # noqa: E402
+
 ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, nargs="+", default=[262144])
 ap.add_argument("--players", type=int, default=2)
-ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--reps", type=int, default=5, help="timed graph replays (each replay is 8-16 launches on cold data)")
 ap.add_argument("--advance", type=int, default=30, help="env-steps played before timing (mid-game states)")
 ap.add_argument("--only", nargs="+", default=None, help="time only these kernels (legal_mask observe step env_step masked_sample)")
 a = ap.parse_args()
 PEAK = 6533.8
-
-
-def timed(fn, reps):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
 
 
 for N in a.envs:
@@ -50,45 +42,16 @@ for N in a.envs:
         obs, rew, term, ill, mask = eng.env_step(learner, sample(mask))
     saved = eng.state.clone()
     act = sample(mask)
-    mask_buf = torch.empty((N, 110), dtype=torch.int32, device=eng.device)
-    obs_buf = torch.empty((N, 265), dtype=torch.float32, device=eng.device)
     res = {}
     want = lambda k: a.only is None or k in a.only  # noqa: E731
     if want("legal_mask"):
-        res["legal_mask"] = (timed(lambda: eng.legal_mask(out=mask_buf), a.reps), W + 440)
+        res["legal_mask"] = (per_launch_ms(torch, eng, saved, lambda o: eng.legal_mask(out=o), ((N, 110), torch.int32), replays=a.reps), W + 440)
     if want("observe"):
-        res["observe"] = (timed(lambda: eng.observe(out=obs_buf), a.reps), W + 1060)
-
-    def timed_after_restore(fn, reps):
-        """state-changing kernels: {restore the saved states; call} captured in a CUDA graph and replayed back to back, minus
-        the restore-only graph (launch by launch from Python the host is slower than a 16 us kernel)"""
-        def graph_ms(body):
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                body()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
-                body()
-            for _ in range(3):
-                g.replay()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                g.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / reps
-
-        return graph_ms(lambda: (eng.state.copy_(saved), fn())) - graph_ms(lambda: eng.state.copy_(saved))
-
+        res["observe"] = (per_launch_ms(torch, eng, saved, lambda o: eng.observe(out=o), ((N, 265), torch.float32), replays=a.reps), W + 1060)
     if want("step"):
-        res["step"] = (timed_after_restore(lambda: eng.step(act), a.reps), 2 * W + 2 + 3)
+        res["step"] = (per_launch_ms(torch, eng, saved, lambda o: eng.step(act), restore=True, replays=a.reps), 2 * W + 2 + 3)
     if want("env_step"):
-        res["env_step"] = (timed_after_restore(lambda: eng.env_step(learner, act), a.reps), 2 * W + 440 + 1060 + 3 + 3)
+        res["env_step"] = (per_launch_ms(torch, eng, saved, lambda o: eng.env_step(learner, act), restore=True, replays=a.reps), 2 * W + 440 + 1060 + 3 + 3)
     for k, (ms, bytes_per_env) in res.items():
         gbs = N * bytes_per_env / (ms * 1e-3) / 1e9
         print(json.dumps({"kernel": k, "envs": N, "players": P, "ms": ms, "envs_per_s": N / (ms * 1e-3), "bytes_per_env": bytes_per_env,
@@ -102,7 +65,19 @@ for N in (a.envs if a.only is None or "masked_sample" in a.only else []):
     logits = torch.randn((rows, 3510), device="cuda")
     eng = pkg.BatchedSplendor(rows, a.players, seed=1)
     mask = eng.legal_mask()
-    ms = timed(lambda: masked_sample(logits, mask, 1, 0), a.reps)
+    def timed(fn, reps=20):  # 3.7 GB of logits per call: the inputs exceed L2 by themselves
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms = timed(lambda: masked_sample(logits, mask, 1, 0))
     n_legal = float(torch.ops.aten.bitwise_and(mask.view(torch.uint8).unsqueeze(-1) >> torch.arange(8, device="cuda", dtype=torch.uint8), 1).sum()) / rows
     b = 440 + 32 * n_legal + 6  # mask bits + one 32-byte sector per legal logit (gather) + action/log-prob out
     print(json.dumps({"kernel": "masked_sample", "envs": rows, "ms": ms, "rows_per_s": rows / (ms * 1e-3), "legal_per_row": n_legal,
