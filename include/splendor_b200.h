@@ -155,6 +155,7 @@ int spl_final_scores(const void *state, int8_t *score2 /*[N][P]*/, uint8_t *outc
 
 /* features.extract_metrics_with_cards(state, seat).astype(float32) (features.py:470-480, splendor_env.py:206):
  * obs[e*265 .. +265].  seat: per-env seat (int8, null = the seat to move). */
+/* (obs: a 16-byte aligned buffer is written with 128-bit stores; a buffer that is only float-aligned works, with scalar stores.) */
 int spl_observe(const void *state, const int8_t *seat, float *obs, int64_t N, int P, void *stream);
 
 /* Whole random playouts that never leave the GPU: Game.Run with RandomAgents (game.py:104-213,
@@ -183,7 +184,9 @@ int spl_playout_from(void *state, const uint8_t *decks, uint64_t seed, uint64_t 
  * seat.  action[e] < 0 = "reset step": only simulate opponents up to the learner's first turn (SplendorEnv.reset).
  * reward[e] int8, terminated[e] u8 (end kind), illegal[e] u8, mask [N][110] u32, obs [N][265] f32 (mask/obs optional).
  * With SPL_F_SELF_PLAY the action is applied for the seat to move (learner may be null), no opponent is simulated, and the
- * mask / observation returned are those of the NEXT seat to move: the caller's policy plays all seats. */
+ * mask / observation returned are those of the NEXT seat to move: the caller's policy plays all seats.
+ * Three kernels in stream order on `stream` (move, observation, mask); an in-kernel opponent's choice is word 0 of the Philox
+ * block (seed, game, total turns so far, stream 0) scaled to its legal count. */
 int spl_env_step(void *state, const uint8_t *decks, uint64_t seed, uint64_t first_game, const uint64_t *game_ids,
                  const int8_t *learner, const int16_t *action, int8_t *reward, uint8_t *terminated, uint8_t *illegal,
                  uint32_t *mask, float *obs, int64_t N, int P, uint32_t flags, void *stream);

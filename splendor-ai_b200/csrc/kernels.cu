@@ -62,7 +62,10 @@ __device__ __forceinline__ void stage_tables(Tables &sT, int bytes = TABLES_RULE
     __syncthreads();
 }
 constexpr int ENV_TB = 256;        // threads per block of the persistent thread-per-env kernels (step, env move)
-constexpr int STEP_BLOCKS_PER_SM = 4, ENV_MOVE_BLOCKS_PER_SM = 3;  // what the register counts (64 / 80) let reside
+// Resident blocks per SM of those kernels, enforced through __launch_bounds__ so that the persistent grids are what actually
+// resides: three blocks = 80 registers per thread.  (Four step blocks = 64 registers spill 40-60 bytes with the decoded row
+// in flight: 0.0143 ms against 0.0132 per 262,144 envs; unconstrained, ptxas took 126 registers and two blocks: 0.0153.)
+constexpr int STEP_BLOCKS_PER_SM = 3, ENV_MOVE_BLOCKS_PER_SM = 3;
 
 // ---------------------------------------------------------------------------------------------- reset / inject
 template <int P>
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(32 * NW, SPL_POOL_BLOCKS_PER_SM) playout_pool_
 // Persistent: the grid is (SMs x resident blocks), every block stages the tables ONCE and strides over the envs; the first
 // env's action and state loads are issued before the table copy and its barrier.
 template <int P>
-__global__ void __launch_bounds__(ENV_TB) step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+__global__ void __launch_bounds__(ENV_TB, STEP_BLOCKS_PER_SM) step_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
                                                       const uint64_t *game_ids, const int16_t *action, int8_t *reward, uint8_t *done, uint8_t *illegal,
                                                       int64_t N, uint32_t flags)
 {
@@ -797,7 +800,7 @@ __global__ void __launch_bounds__(TILE_TB_MAX) observe_kernel(const uint4 *state
 // three was slower (0.214 ms against 0.16 ms per 262,144 envs) because the shared-memory tile of the row kernels caps
 // residency at 14 warps per SM, and this latency-bound part then runs at that occupancy too.
 template <int P>
-__global__ void __launch_bounds__(ENV_TB) env_move_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
+__global__ void __launch_bounds__(ENV_TB, ENV_MOVE_BLOCKS_PER_SM) env_move_kernel(uint4 *state, const uint8_t *decks, uint64_t seed, uint64_t first_game,
                                                           const uint64_t *game_ids, const int8_t *learner, const int16_t *action,
                                                           int8_t *reward, uint8_t *terminated, uint8_t *illegal, int64_t N, uint32_t flags)
 {
