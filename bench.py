@@ -93,7 +93,40 @@ def _python_engine_worker(args):
     return steps, games, time.perf_counter() - t0
 
 
-def python_engine_throughput(P, seconds=12.0):
+def _python_env_worker(args):
+    """One process: the UNMODIFIED reference SplendorEnv (gym/envs/splendor_env.py:27-245) with RandomAgent opponents, stepped
+    the way the PPO rollout does - env.get_legal_actions_mask(), a uniform legal action, env.step(action) - for `seconds`.
+    `gymnasium` is absent on these boxes: the 25-line stand-in of oracle/ref_harness.py (Env / spaces / register) is installed
+    first, as SURVEY.md 8(c) describes."""
+    path, P, seconds, seed = args
+    sys.path.insert(0, path)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import random
+
+    import numpy as np
+    import ref_harness
+
+    ref_harness._install_gymnasium_stub()
+    from splendor.agents.generic.random import myAgent
+    from splendor.splendor.gym.envs.splendor_env import SplendorEnv
+
+    random.seed(seed)
+    rng = np.random.default_rng(seed)
+    env = SplendorEnv([myAgent(0) for _ in range(P - 1)])
+    calls = episodes = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        env.reset(seed=seed + episodes)
+        terminated = False
+        while not terminated and time.perf_counter() - t0 < seconds:
+            legal = np.nonzero(env.get_legal_actions_mask())[0]
+            _, _, terminated, _, _ = env.step(int(rng.choice(legal)))
+            calls += 1
+        episodes += 1
+    return calls, episodes, time.perf_counter() - t0
+
+
+def python_engine_throughput(P, seconds=12.0, env=False):
     """The reference's own Python engine on every host core of THIS box, in the same run (north_star: "the reference's
     Python engine timed on the same box's host cores in the same run, with the core count stated").  None if absent."""
     for path in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference/src"):
@@ -106,11 +139,16 @@ def python_engine_throughput(P, seconds=12.0):
     cores = os.cpu_count() or 1
     try:
         with mp.get_context("spawn").Pool(cores) as pool:
-            res = pool.map(_python_engine_worker, [(path, P, seconds, 1000 + i) for i in range(cores)])
+            res = pool.map(_python_env_worker if env else _python_engine_worker, [(path, P, seconds, 1000 + i) for i in range(cores)])
     except Exception as exc:  # a reported baseline must never fail the line
         return {"python_reference": "failed: " + repr(exc)[:200]}
     steps, games = sum(r[0] for r in res), sum(r[1] for r in res)
     dt = max(r[2] for r in res)
+    if env:
+        return {"value": steps / dt, "unit": "env.step calls/s", "cores": cores, "per_core": steps / dt / cores, "kind": "reference",
+                "sample": f"unmodified SplendorEnv (mask + step, RandomAgent opponents, {P} players) from "
+                          f"{os.path.relpath(path, ROOT) if path.startswith(ROOT) else path}, {steps} calls in {games} episodes, "
+                          f"{dt:.1f} s on {cores} processes"}
     return {"value": steps / dt, "unit": UNIT, "cores": cores, "per_core": steps / dt / cores, "kind": "reference",
             "sample": f"unmodified SplendorGameRule + RandomAgent loop from {os.path.relpath(path, ROOT) if path.startswith(ROOT) else path}, "
                       f"{games} games ({steps} env-steps) in {dt:.1f} s on {cores} processes"}
@@ -524,6 +562,9 @@ def run_b200(args):
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": f"{games} of the workload's games ({steps} env-steps) in {dt:.1f} s on {cores} host threads"}
         out["cpu_baseline_python"] = python_engine_throughput(P, min(args.cpu_seconds, 15.0))
+        # the same for 4 players, and the reference's SplendorEnv calls/s beside config 4's fused env-step call
+        out["cpu_baseline_python_4p"] = python_engine_throughput(4, min(args.cpu_seconds, 15.0) / 2)
+        out["cpu_baseline_python_env"] = python_engine_throughput(2, min(args.cpu_seconds, 15.0) / 2, env=True)
     return json.dumps(out)
 
 
