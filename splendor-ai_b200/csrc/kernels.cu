@@ -2,18 +2,20 @@
 //
 //   playout_pool_kernel a block owns a POOL of up to 640 games: between rounds the live games sit in shared memory as a
 //                       dense list, in a round each warp plays 8 moves of 32 of them out of registers (terminal test, legal
-//                       count, Philox choice, k-th legal action, apply, lazy deal), survivors are compacted into the next
+//                       count, choice by the round's Philox words, k-th legal action, apply, lazy deal), survivors are compacted into the next
 //                       list, finished games are scored, a keeper warp tops the list up with new games.  No HBM traffic
 //                       inside the loop except the optional trace.
-//   legal_mask_kernel   persistent; one thread builds one env's 3510-bit row in registers (32/64-bit group patterns) and
-//                       flushes finished words into its warp's dense shared-memory tile; lane 0 sends the warp's 32 rows
-//                       (14,080 contiguous bytes) to HBM with one bulk copy (cp.async.bulk) while the warp moves on.
-//   step_kernel         thread-per-env, persistent: decode the ALL_ACTIONS index, membership test, apply, reward / done / illegal.
-//   observe_kernel      same scheme for the 265-float observation: rows staged as bytes, widened to float32 on the way
-//                       out with coalesced stores, warp by warp (no block barrier).
+//   legal_mask_kernel   persistent, software-pipelined state loads; one thread builds one env's 3510-bit row in registers
+//                       (32/64-bit group patterns) and flushes finished words into its warp's dense shared-memory tile;
+//                       lane 0 sends the warp's 32 rows (14,080 contiguous bytes) to HBM with one bulk copy (cp.async.bulk)
+//                       while the warp moves on.
+//   step_kernel         thread-per-env, persistent: the ALL_ACTIONS index decoded by table, membership test, apply,
+//                       reward / done / illegal.
+//   observe_kernel      same scheme for the 265-float observation: rows staged as DENSE bytes, the warp's 32 rows widened
+//                       to float32 as one flat span with 128-bit stores (no block barrier).
 //   env_move_kernel     the PPO rollout call's first part: learner move + in-kernel random opponents, thread-per-env,
-//                       persistent; spl_env_step then runs observe_kernel and legal_mask_kernel for the learner's seat on
-//                       two streams.
+//                       persistent; spl_env_step then runs observe_kernel and legal_mask_kernel for the learner's seat in
+//                       stream order.
 //   reset / inject / final_scores: thread-per-env.
 #include <cuda_runtime.h>
 #include <stddef.h>
