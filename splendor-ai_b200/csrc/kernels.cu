@@ -823,7 +823,7 @@ __global__ void __launch_bounds__(ENV_TB, ENV_MOVE_BLOCKS_PER_SM) env_move_kerne
     __syncthreads();
     while (i < N) {
         if (self_play) me = seat_of(e.meta);
-        const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i};
+        const DeckSrc src{decks ? decks + i * SPL_DECK_BYTES : nullptr, seed, game_ids ? game_ids[i] : first_game + (uint64_t)i, nullptr, &sT};  // (the table form of the k-th-bit select for lazy deals)
         int rew = 0, bad = 0;
         bool go = true;
         if (a >= 0) {
