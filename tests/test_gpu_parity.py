@@ -476,6 +476,29 @@ def test_results_do_not_depend_on_the_launch_geometry(pkg, oracle):
     assert int(whole["counters"][0]) == G
 
 
+def test_row_kernels_do_not_depend_on_the_launch_shape(pkg):
+    """The mask and observation kernels are persistent: the host picks (warps per block) x (blocks per SM) per batch size, and
+    SPL_MASK_SHAPE / SPL_OBS_SHAPE override it.  Every shape - one warp per block, blocks that split a tile row between
+    neighbours differently, more blocks than tiles - must write the same bits."""
+    N, P = 5003, 3  # ragged: the last tile has 11 rows
+    eng = pkg.BatchedSplendor(N, P, seed=21, first_game=77, limit_rounds=True)
+    learner = torch.zeros(N, dtype=torch.int8, device=eng.device)
+    act = torch.full((N,), -1, dtype=torch.int16, device=eng.device)
+    gen = torch.Generator(device=eng.device).manual_seed(5)
+    for _ in range(10):
+        _, _, _, _, mask = eng.env_step(learner, act)
+        act = torch.multinomial(pkg.env.unpack_mask(mask, torch.float32), 1, generator=gen).squeeze(1).to(torch.int16)
+    want_mask, want_obs = eng.legal_mask().clone(), eng.observe().clone()
+    try:
+        for shape in ("1x1", "1x4", "2x3", "3x7", "4x5", "5x4", "7x2", "13x1", "16x1"):
+            os.environ["SPL_MASK_SHAPE"] = os.environ["SPL_OBS_SHAPE"] = shape
+            assert torch.equal(eng.legal_mask(), want_mask), shape
+            assert torch.equal(eng.observe().view(torch.int32), want_obs.view(torch.int32)), shape
+    finally:
+        os.environ.pop("SPL_MASK_SHAPE", None)
+        os.environ.pop("SPL_OBS_SHAPE", None)
+
+
 def test_two_devices_from_one_process(pkg, oracle):
     """The library keeps its staging memory, events and SM count PER DEVICE: one process drives two GPUs through the
     host-buffer calls and the device-pointer calls alternately (skipped on a one-GPU box)."""
