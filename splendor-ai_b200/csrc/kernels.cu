@@ -1046,10 +1046,11 @@ static int launch_pool_nw(const PlayoutArgs &a, cudaStream_t stream)
     kernel<<<grid, 32 * NW, sizeof(Sm), stream>>>(a);
     return SPL_OK;
 }
-// Two pool sizes: 20 warps per block (19 stepping) for launches that keep the pools refilled, and 19 warps (104 instead
-// of 96 registers per thread: no spills, a slightly shorter step) for launches whose games all fit the pools at once, where
-// the time is set by the latency of the rounds, not by the issue rate (65,536 games: 0.3917 -> 0.3866 ms; 2^20 games:
-// 2.076 -> 2.072e10 the other way, profiles/r2_playout.md).
+// Two pool sizes: 20 warps per block (19 stepping) for launches that keep the pools refilled, and 19 warps (a budget of
+// 104 instead of 96 registers per thread) for launches whose games all fit the pools at once, where the time is set by
+// the latency of the rounds, not by the issue rate (measured when the step still spilled at 96 registers: 65,536 games
+// 0.3917 -> 0.3866 ms; 2^20 games 2.076 -> 2.072e10 the other way, profiles/r2_playout.md; the step now takes ~90, and the
+// smaller pool still wins for 4 players: 65,536 games 0.636 -> 0.626 ms).
 template <int P, int MODE>
 static int launch_pool(const PlayoutArgs &a, cudaStream_t stream)
 {
