@@ -312,7 +312,8 @@ __global__ void __launch_bounds__(32 * NW, SPL_POOL_BLOCKS_PER_SM) playout_pool_
                     S.rnd[threadIdx.x][0] = philox_rk(a.rk, game, blk, STREAM_ACTION);
                     S.rnd[threadIdx.x][1] = philox_rk(a.rk, game, blk + 1, STREAM_ACTION);
                     if ((t & 3) + n_steps > 8) S.rnd[threadIdx.x][2] = philox_rk(a.rk, game, blk + 2, STREAM_ACTION);
-                    const uint32_t *draws = reinterpret_cast<const uint32_t *>(&S.rnd[threadIdx.x][0]) - 4 * blk;  // draws[t]
+                    const uint32_t *draws = reinterpret_cast<const uint32_t *>(&S.rnd[threadIdx.x][0]);  // move t: draws[t - t_blk]
+                    const int t_blk = (int)(4u * blk);
 #pragma unroll 1
                     for (int s = 0; s < n_steps && kind == SPL_END_NONE; s++) {
                         Ctx c;
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(32 * NW, SPL_POOL_BLOCKS_PER_SM) playout_pool_
                         Choice ch;
                         make_ctx<P, true>(e, T, c);
                         const int total = count_legal(e, T, c, f);
-                        const uint32_t r = draws[t];
+                        const uint32_t r = draws[t - t_blk];
                         select_legal(e, T, c, f, total, (int)__umulhi(r, (uint32_t)(total ? total : c.nS)), ch);
                         if (__builtin_expect(t < a.trace_len, 0)) a.trace[(int64_t)t * a.n_games + gid] = (int16_t)ch.idx;
                         apply_action<P, false, true>(e, ch, src);
